@@ -1,0 +1,163 @@
+/* vtts_b200.h -- C ABI of libvtts_b200.so (B200 / sm_100a synthesis hot path).
+ *
+ * The reference (ducnt18121997/Viet-Transformer-TTS) is pure Python/PyTorch and has no FFI
+ * layer; its boundary for this path is the nn.Module surface.  Each entry point below names
+ * the reference interface it replaces (paths relative to the reference root).  The Python
+ * module shells in viet-transformer-tts_b200/vtts_b200/ bind these with ctypes; the stub a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative VTTS_E_* code on failure;
+ *    vtts_last_error() returns a thread-local message for the last failure on this thread;
+ *  - nothing throws, nothing allocates activation memory: inputs, outputs and workspaces are
+ *    raw device pointers owned by the caller (PyTorch); handles own only packed weights;
+ *  - every launch goes to the caller's stream (pass torch.cuda.current_stream().cuda_stream);
+ *    no hidden synchronisation;
+ *  - one VttsGen handle per (device, module); a handle is not thread-safe, distinct handles are.
+ */
+#ifndef VTTS_B200_H_
+#define VTTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTTS_VERSION 100 /* 0.1.0 */
+
+#define VTTS_OK 0
+#define VTTS_E_INVALID (-1)     /* bad argument / unsupported configuration */
+#define VTTS_E_CUDA (-2)        /* CUDA runtime / driver error */
+#define VTTS_E_WORKSPACE (-3)   /* workspace too small */
+#define VTTS_E_STATE (-4)       /* handle not ready (weights missing) */
+#define VTTS_E_UNSUPPORTED (-5) /* valid configuration this build has no kernel for */
+
+typedef void *vtts_stream_t; /* cudaStream_t */
+
+int vtts_version(void);
+const char *vtts_last_error(void);
+/* Compute capability major*10+minor of the current device, or a negative code. */
+int vtts_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * LengthRegulator -- replaces models/tts/fastspeech2/layers.py:434-462
+ * (LengthRegulator.forward) and the pad_list it calls (fastspeech2/function.py:97-124).
+ * ---------------------------------------------------------------------------------------- */
+
+/* layers.py:446-448  ds = torch.round(ds.float() * alpha).long()   (n = B*Tmax elements). */
+int vtts_lr_scale_durations(const int64_t *ds, int64_t n, float alpha, int64_t *out,
+                            vtts_stream_t stream);
+
+/* Caller-side mel_lens = torch.sum(ds, dim=1) (layers.py:209) plus the three scalars the
+ * host needs for pad_list's max_len and the ds.sum()==0 test (layers.py:450):
+ *   stats[0] = max_b mel_len[b], stats[1] = sum_b mel_len[b], stats[2] = #negative durations.
+ * mel_len may be NULL.  stats (device, 3 x int64) is zeroed by this call. */
+int vtts_lr_rowsum(const int64_t *ds, int B, int Tmax, int64_t *mel_len, int64_t *stats,
+                   vtts_stream_t stream);
+
+/* layers.py:458  ds[ds.sum(dim=1).eq(0)] = 1   (in place on the caller's tensor). */
+int vtts_lr_fix_zero_rows(int64_t *ds, int B, int Tmax, vtts_stream_t stream);
+
+/* layers.py:460-462  repeat_interleave each row, pad_list to T_out.
+ * xs (B,Tmax,D) and out (B,T_out,D) are contiguous arrays of elem_size-byte elements
+ * (1,2,4 or 8); pad points at ONE element's bytes on the host.  Bit-exact copy. */
+int vtts_lr_gather(const void *xs, const int64_t *ds, void *out, int B, int Tmax, int D,
+                   int64_t T_out, int elem_size, const void *pad, vtts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HiFi-GAN generator -- replaces models/gan_tts/hifigan/generator.py:132-156
+ * (HiFiGAN.forward), layers.py:83-98 (ResidualBlock.forward) and the vits2 skin
+ * models/gan_tts/vits2/layers.py:159-177 (Generator.forward), sublayers.py:293-303,341-349.
+ * ---------------------------------------------------------------------------------------- */
+
+#define VTTS_MAX_STAGES 8
+#define VTTS_MAX_BLOCKS 8
+#define VTTS_MAX_DILATIONS 8
+
+typedef struct VttsGenConfig {
+    int32_t in_channels;      /* generator.py:21  (80; 384 for JETS; 192 for vits2) */
+    int32_t out_channels;     /* generator.py:22  (1) */
+    int32_t channels;         /* generator.py:23  (512) */
+    int32_t global_channels;  /* generator.py:24  (-1/0 = none) */
+    int32_t kernel_size;      /* generator.py:25  input/output conv kernel (7) */
+    int32_t num_upsamples;    /* len(upsample_scales) */
+    int32_t upsample_scales[VTTS_MAX_STAGES];
+    int32_t upsample_kernel_sizes[VTTS_MAX_STAGES];
+    int32_t upsample_paddings[VTTS_MAX_STAGES];        /* ESPnet: s/2+s%2; vits2: (k-u)/2 */
+    int32_t upsample_output_paddings[VTTS_MAX_STAGES]; /* ESPnet: s%2;     vits2: 0 */
+    int32_t num_blocks;       /* len(resblock_kernel_sizes) */
+    int32_t resblock_kernel_sizes[VTTS_MAX_BLOCKS];
+    int32_t num_dilations[VTTS_MAX_BLOCKS];
+    int32_t resblock_dilations[VTTS_MAX_BLOCKS][VTTS_MAX_DILATIONS];
+    int32_t use_additional_convs; /* 1: ResidualBlock/ResBlock1 (conv pairs); 0: ResBlock2 */
+    float lrelu_slope;            /* 0.1 */
+    float final_lrelu_slope;      /* 0.01 (nn.LeakyReLU() default, generator.py:111) */
+} VttsGenConfig;
+
+typedef struct VttsGen VttsGen;
+
+/* Layer enumeration.  Layers are numbered in reference construction order:
+ *   0                      input_conv            (generator.py:70)
+ *   per stage i:           upsamples[i][1]       (generator.py:86)  kind 1
+ *     per block j, unit m: blocks[n].convs1[m][1] then convs2[m][1] (layers.py:48-81)
+ *   then                   output_conv[1]        (generator.py:113)
+ *   then (if any)          global_conv           (generator.py:123) */
+typedef struct VttsLayerInfo {
+    int32_t kind;        /* 0 Conv1d, 1 ConvTranspose1d */
+    int32_t cin, cout, ksize, dilation;
+    int32_t stage;       /* -1 pre, num_upsamples post/global */
+    int32_t block, unit, which; /* which: 1 = convs1, 2 = convs2; -1 n/a */
+} VttsLayerInfo;
+
+int vtts_gen_create(const VttsGenConfig *cfg, VttsGen **out);
+int vtts_gen_destroy(VttsGen *h);
+int vtts_gen_num_layers(const VttsGen *h);
+int vtts_gen_layer_info(const VttsGen *h, int layer, VttsLayerInfo *info);
+
+/* Upload one layer.  `weight_v` is the layer's weight in the reference's own layout
+ * (Conv1d (cout,cin,k); ConvTranspose1d (cin,cout,k)), fp32, device memory.  If `weight_g`
+ * is non-NULL the weight-norm is folded on the device, w = g * v / ||v||_(1,2) per dim-0
+ * index (torch.nn.utils.weight_norm, generator.py:192); NULL means `weight_v` is the plain
+ * weight (after remove_weight_norm, generator.py:173-183).  bias may be NULL (vits2 conv_post).
+ * Packs the fp32 and the bf16 tensor-core copies. */
+int vtts_gen_load_layer(VttsGen *h, int layer, const float *weight_v, const float *weight_g,
+                        const float *bias, vtts_stream_t stream);
+
+#define VTTS_PRECISION_FP32 0 /* CUDA-core fp32 direct convolution (in-repo reference path) */
+#define VTTS_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate/residual, fp32 output conv */
+
+int vtts_gen_workspace_bytes(const VttsGen *h, int B, int T, int precision, size_t *bytes);
+
+/* c (B,in_channels,T) fp32 channels-first, g (B,global_channels) fp32 or NULL,
+ * wav (B,out_channels,T*upsample_factor) fp32.  dump_stage >= 0 additionally copies an
+ * intermediate tensor to dump_out as (B,C,L) fp32 channels-first:
+ *   0 = input_conv output, 2i+1 = upsamples[i] output, 2i+2 = MRF mean of stage i. */
+int vtts_gen_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, int T,
+                     void *workspace, size_t workspace_bytes, int precision, int dump_stage,
+                     float *dump_out, vtts_stream_t stream);
+
+/* Number of kernel launches the last vtts_gen_forward on this handle issued. */
+int vtts_gen_last_launch_count(const VttsGen *h);
+
+/* ------------------------------------------------------------------------------------------
+ * Test hooks (used by tests/ only): single-layer entry points.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Plain fp32 Conv1d on channels-first tensors with the fused options the generator uses.
+ * y = [tanh]( (conv(lrelu_in(x)) + bias [+ res]) ) ; slope_in == 1 disables the activation. */
+int vtts_dbg_conv1d_fp32(const float *x, const float *w, const float *bias, const float *res,
+                         float *y, int B, int cin, int cout, int L, int ksize, int dilation,
+                         float slope_in, int apply_tanh, vtts_stream_t stream);
+
+/* tcgen05 self-test: D[M,N] = A[M,K] * B[N,K]^T with bf16 operands (K-major, TMA SW128),
+ * optional row shift of the A descriptor (exercises the halo-reuse addressing used by the
+ * convolution kernels).  variant selects descriptor construction options. */
+int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float *d, int M, int N, int K,
+                       int a_rows_total, int row_shift, int variant, vtts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTTS_B200_H_ */

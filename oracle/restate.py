@@ -1,0 +1,279 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the synthesis hot path.
+
+This file is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The product package
+(``viet-transformer-tts_b200/``) never does and fails loudly without its CUDA library.
+
+Pinning: the reference ships no golden vectors, so this restatement is
+pinned by executing the unmodified reference modules in the build container
+(``oracle/ref_loader.py``) -- ``tests/test_oracle_pinned.py`` compares them directly when
+``/root/reference`` exists, and ``tests/golden/*.npz`` (made by ``tests/golden/make_golden.py``
+from the reference itself) travel to the GPU box.  JETS-specific composition is *parity
+unpinned* (espnet is not vendored).
+
+Every function cites the reference lines it restates (paths relative to the reference root).
+The LengthRegulator is integer/byte work and is restated with numpy index arithmetic (and in
+plain C in ``oracle/lr_oracle.c``); the generator is floating point and is restated with
+``torch.nn.functional`` on the CPU in fp32 or fp64.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------
+# LengthRegulator  (models/tts/fastspeech2/layers.py:434-462, pad_list function.py:97-124)
+# --------------------------------------------------------------------------------------------
+
+
+def lr_scale_durations(ds: torch.Tensor, alpha: float) -> torch.Tensor:
+    """layers.py:446-448 -- ``ds = torch.round(ds.float() * alpha).long()`` (half-to-even)."""
+    assert alpha > 0
+    d32 = ds.detach().cpu().numpy().astype(np.float32)
+    scaled = (d32 * np.float32(alpha)).astype(np.float32)
+    return torch.from_numpy(np.rint(scaled).astype(np.int64))
+
+
+def lr_expand(xs: torch.Tensor, ds: torch.Tensor, alpha: float = 1.0, pad_value: float = 0.0):
+    """Restates ``LengthRegulator.forward`` (layers.py:434-462).
+
+    Returns ``(out, ds_used)``.  ``ds`` is mutated IN PLACE on the all-zero-batch path exactly
+    like the reference (layers.py:450-458): when the *whole batch* sums to zero every element
+    of every all-zero row becomes 1.  ``out[b, t] = xs[b, j]`` with
+    ``j = #{i : cumsum(ds[b])[i] <= t}`` for ``t < sum(ds[b])`` else ``pad_value``;
+    ``T_out = max_b sum(ds[b])`` (pad_list, function.py:117-122).
+    """
+    if alpha != 1.0:
+        ds = lr_scale_durations(ds, alpha)
+    if int(ds.sum()) == 0:
+        logging.warning(
+            "predicted durations includes all 0 sequences. fill the first element with 1."
+        )
+        ds[ds.sum(dim=1).eq(0)] = 1
+    d = ds.detach().cpu().numpy().astype(np.int64)
+    if (d < 0).any():
+        raise RuntimeError("repeats can not be negative")  # torch.repeat_interleave contract
+    x = xs.detach().cpu().numpy()
+    B, Tmax = d.shape
+    lens = d.sum(axis=1)
+    T_out = int(lens.max()) if B > 0 else 0
+    out = np.full((B, T_out) + x.shape[2:], pad_value, dtype=x.dtype)
+    for b in range(B):
+        cum = np.cumsum(d[b])
+        t = np.arange(int(lens[b]), dtype=np.int64)
+        j = np.searchsorted(cum, t, side="right")  # first index with cum > t
+        out[b, : int(lens[b])] = x[b, j]
+    return torch.from_numpy(out), ds
+
+
+def lr_mel_len(ds: torch.Tensor) -> torch.Tensor:
+    """``mel_lens = torch.sum(duration_rounded, dim=1)`` -- VarianceAdaptor, layers.py:209."""
+    return torch.from_numpy(ds.detach().cpu().numpy().astype(np.int64).sum(axis=1))
+
+
+def durations_from_log(log_d: torch.Tensor, d_control: float = 1.0) -> torch.Tensor:
+    """layers.py:205-208 -- ``clamp(round(exp(logd) - 1) * d_control, min=0).long()``."""
+    return torch.clamp(torch.round(torch.exp(log_d) - 1) * d_control, min=0).long()
+
+
+# --------------------------------------------------------------------------------------------
+# weight-norm folding  (generator.py:185-195 -> torch.nn.utils.weight_norm, dim=0)
+# --------------------------------------------------------------------------------------------
+
+
+def fold_weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """``w = g * v / ||v||`` with the norm over dims (1, 2) per dim-0 index.
+
+    dim 0 is the *out* channel for Conv1d and the *in* channel for ConvTranspose1d
+    (SURVEY.md appendix 9.5).
+    """
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
+    return v * (g / norm)
+
+
+def _weight(sd: Dict[str, torch.Tensor], prefix: str) -> torch.Tensor:
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"]
+    return fold_weight_norm(sd[prefix + ".weight_g"], sd[prefix + ".weight_v"])
+
+
+def _bias(sd: Dict[str, torch.Tensor], prefix: str) -> Optional[torch.Tensor]:
+    return sd.get(prefix + ".bias")
+
+
+# --------------------------------------------------------------------------------------------
+# HiFiGAN (ESPnet skin)  generator.py:132-156, ResidualBlock layers.py:83-98
+# --------------------------------------------------------------------------------------------
+
+
+def residual_block(
+    sd, prefix: str, x: torch.Tensor, kernel_size: int, dilations: Sequence[int],
+    slope: float = 0.1, use_additional_convs: bool = True,
+) -> torch.Tensor:
+    """layers.py:93-97: ``xt = convs2[i](convs1[i](x)); x = xt + x`` (each = LeakyReLU + Conv1d)."""
+    for idx, d in enumerate(dilations):
+        xt = F.conv1d(
+            F.leaky_relu(x, slope), _weight(sd, f"{prefix}.convs1.{idx}.1"),
+            _bias(sd, f"{prefix}.convs1.{idx}.1"), padding=(kernel_size - 1) // 2 * d, dilation=d,
+        )
+        if use_additional_convs:
+            xt = F.conv1d(
+                F.leaky_relu(xt, slope), _weight(sd, f"{prefix}.convs2.{idx}.1"),
+                _bias(sd, f"{prefix}.convs2.{idx}.1"), padding=(kernel_size - 1) // 2,
+            )
+        x = xt + x
+    return x
+
+
+def hifigan_forward(
+    sd: Dict[str, torch.Tensor], c: torch.Tensor, g: Optional[torch.Tensor] = None,
+    upsample_scales: Sequence[int] = (8, 8, 2, 2),
+    resblock_kernel_sizes: Sequence[int] = (3, 7, 11),
+    resblock_dilations: Sequence[Sequence[int]] = ((1, 3, 5), (1, 3, 5), (1, 3, 5)),
+    kernel_size: int = 7, slope: float = 0.1, use_additional_convs: bool = True,
+    dtype: torch.dtype = torch.float32, return_stages: bool = False,
+):
+    """Restates ``HiFiGAN.forward`` (generator.py:132-156) from a reference ``state_dict``.
+
+    (B, in_ch, T) -> (B, out_ch, T * prod(scales)).  The final activation slope is the
+    ``nn.LeakyReLU()`` default 0.01 (generator.py:111), not ``slope``.
+    """
+    sd = {k: v.detach().to("cpu", dtype) for k, v in sd.items()}
+    c = c.detach().to("cpu", dtype)
+    stages: List[torch.Tensor] = []
+    c = F.conv1d(c, _weight(sd, "input_conv"), _bias(sd, "input_conv"), padding=(kernel_size - 1) // 2)
+    if g is not None:
+        c = c + F.conv1d(g.detach().to("cpu", dtype), _weight(sd, "global_conv"), _bias(sd, "global_conv"))
+    stages.append(c)
+    nb = len(resblock_kernel_sizes)
+    for i, s in enumerate(upsample_scales):
+        c = F.conv_transpose1d(
+            F.leaky_relu(c, slope), _weight(sd, f"upsamples.{i}.1"), _bias(sd, f"upsamples.{i}.1"),
+            stride=s, padding=s // 2 + s % 2, output_padding=s % 2,
+        )
+        stages.append(c)
+        cs = 0.0
+        for j in range(nb):
+            cs = cs + residual_block(
+                sd, f"blocks.{i * nb + j}", c, resblock_kernel_sizes[j], resblock_dilations[j],
+                slope, use_additional_convs,
+            )
+        c = cs / nb
+        stages.append(c)
+    c = torch.tanh(
+        F.conv1d(F.leaky_relu(c, 0.01), _weight(sd, "output_conv.1"), _bias(sd, "output_conv.1"),
+                 padding=(kernel_size - 1) // 2)
+    )
+    return (c, stages) if return_stages else c
+
+
+def hifigan_inference(sd, c: torch.Tensor, g: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+    """generator.py:197-213: (T, in_ch) -> (T * upsample_factor, out_ch)."""
+    if g is not None:
+        g = g.unsqueeze(0)
+    y = hifigan_forward(sd, c.transpose(1, 0).unsqueeze(0), g=g, **kw)
+    return y.squeeze(0).transpose(1, 0)
+
+
+# --------------------------------------------------------------------------------------------
+# vits2 Generator skin  (vits2/layers.py:159-177, ResBlock1/2 sublayers.py:293-303, 341-349)
+# --------------------------------------------------------------------------------------------
+
+
+def vits2_generator_forward(
+    sd: Dict[str, torch.Tensor], x: torch.Tensor, g: Optional[torch.Tensor] = None,
+    resblock: str = "1", upsample_rates: Sequence[int] = (8, 8, 2, 2),
+    upsample_kernel_sizes: Sequence[int] = (16, 16, 4, 4),
+    resblock_kernel_sizes: Sequence[int] = (3, 7, 11),
+    resblock_dilation_sizes: Sequence[Sequence[int]] = ((1, 3, 5), (1, 3, 5), (1, 3, 5)),
+    dtype: torch.dtype = torch.float32,
+) -> torch.Tensor:
+    """Restates vits2 ``Generator.forward``: conv_pre/conv_post carry no weight-norm, conv_post
+    has no bias (layers.py:153), ups padding is ``(k - u) // 2`` (layers.py:140)."""
+    sd = {k: v.detach().to("cpu", dtype) for k, v in sd.items()}
+    x = x.detach().to("cpu", dtype)
+    x = F.conv1d(x, _weight(sd, "conv_pre"), _bias(sd, "conv_pre"), padding=3)
+    if g is not None:
+        x = x + F.conv1d(g.detach().to("cpu", dtype), _weight(sd, "cond"), _bias(sd, "cond"))
+    nk = len(resblock_kernel_sizes)
+    for i, (u, k) in enumerate(zip(upsample_rates, upsample_kernel_sizes)):
+        x = F.leaky_relu(x, 0.1)
+        x = F.conv_transpose1d(x, _weight(sd, f"ups.{i}"), _bias(sd, f"ups.{i}"), stride=u, padding=(k - u) // 2)
+        xs = None
+        for j in range(nk):
+            p = f"resblocks.{i * nk + j}"
+            ks, dil = resblock_kernel_sizes[j], resblock_dilation_sizes[j]
+            y = x
+            if resblock == "1":
+                for m, d in enumerate(dil):
+                    xt = F.conv1d(F.leaky_relu(y, 0.1), _weight(sd, f"{p}.convs1.{m}"), _bias(sd, f"{p}.convs1.{m}"),
+                                  padding=(ks * d - d) // 2, dilation=d)
+                    xt = F.conv1d(F.leaky_relu(xt, 0.1), _weight(sd, f"{p}.convs2.{m}"), _bias(sd, f"{p}.convs2.{m}"),
+                                  padding=(ks - 1) // 2)
+                    y = xt + y
+            else:
+                for m, d in enumerate(dil):
+                    xt = F.conv1d(F.leaky_relu(y, 0.1), _weight(sd, f"{p}.convs.{m}"), _bias(sd, f"{p}.convs.{m}"),
+                                  padding=(ks * d - d) // 2, dilation=d)
+                    y = xt + y
+            xs = y if xs is None else xs + y
+        x = xs / nk
+    x = F.leaky_relu(x)  # default slope 0.01, layers.py:174
+    x = F.conv1d(x, _weight(sd, "conv_post"), None, padding=3)
+    return torch.tanh(x)
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic state_dicts (same key set / shapes as the reference constructors)
+# --------------------------------------------------------------------------------------------
+
+
+def make_hifigan_state_dict(
+    in_channels: int = 80, out_channels: int = 1, channels: int = 512, global_channels: int = -1,
+    kernel_size: int = 7, upsample_scales: Sequence[int] = (8, 8, 2, 2),
+    resblock_kernel_sizes: Sequence[int] = (3, 7, 11),
+    resblock_dilations: Sequence[Sequence[int]] = ((1, 3, 5), (1, 3, 5), (1, 3, 5)),
+    use_additional_convs: bool = True, seed: int = 1234, weight_norm: bool = True,
+) -> Dict[str, torch.Tensor]:
+    """Random-init ``state_dict`` with the reference's key names and shapes (generator.py:70-123).
+
+    Values are Kaiming-uniform-like (what the reference effectively has) but are
+    drawn by this function, not by the reference constructor -- use the reference's own
+    ``state_dict()`` (tests/golden) when bit-identical weights matter.
+    """
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(prefix, cout, cin, k, transpose=False):
+        shape = (cin, cout, k) if transpose else (cout, cin, k)
+        fan_in = shape[1] * k
+        bound = 1.0 / np.sqrt(fan_in)
+        w = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+        b = (torch.rand(cout, generator=gen) * 2 - 1) * bound
+        if weight_norm:
+            sd[prefix + ".weight_g"] = w.reshape(shape[0], -1).norm(dim=1).reshape(-1, 1, 1) * (
+                0.75 + 0.5 * torch.rand(shape[0], 1, 1, generator=gen))
+            sd[prefix + ".weight_v"] = w
+        else:
+            sd[prefix + ".weight"] = w
+        sd[prefix + ".bias"] = b
+
+    conv("input_conv", channels, in_channels, kernel_size)
+    ch = channels
+    for i, s in enumerate(upsample_scales):
+        conv(f"upsamples.{i}.1", ch // 2, ch, 2 * s, transpose=True)
+        ch //= 2
+        for j, k in enumerate(resblock_kernel_sizes):
+            n = i * len(resblock_kernel_sizes) + j
+            for m in range(len(resblock_dilations[j])):
+                conv(f"blocks.{n}.convs1.{m}.1", ch, ch, k)
+                if use_additional_convs:
+                    conv(f"blocks.{n}.convs2.{m}.1", ch, ch, k)
+    conv("output_conv.1", out_channels, ch, kernel_size)
+    if global_channels > 0:
+        conv("global_conv", channels, global_channels, 1)
+    return sd

@@ -1,0 +1,151 @@
+"""Generate the golden vectors under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or fixtures, so these files -- produced by
+executing the reference's own modules (oracle/ref_loader.py) on seeded synthetic inputs -- are
+what pins both the CPU oracle (oracle/restate.py, oracle/lr_oracle.c) and the CUDA path.  They
+travel to the GPU box, where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_loader  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+logging.disable(logging.WARNING)
+
+
+def sd_to_np(sd, prefix="sd."):
+    return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def lr_cases():
+    LR = ref_loader.load_length_regulator()
+    g = torch.Generator().manual_seed(0)
+    cases = {}
+
+    def add(name, xs, ds, alpha=1.0, pad=0.0):
+        ds_in = ds.clone()
+        ds_work = ds.clone()
+        out = LR(pad_value=pad)(xs, ds_work, alpha)
+        cases[name] = dict(xs=xs.numpy(), ds=ds_in.numpy(), ds_after=ds_work.numpy(), out=out.numpy(),
+                           alpha=np.float64(alpha), pad=np.float64(pad))
+
+    # plain ragged batch, zeros on the padding
+    B, T, D = 4, 13, 80
+    ds = torch.randint(1, 12, (B, T), generator=g)
+    for b, n in enumerate([13, 9, 5, 1]):
+        ds[b, n:] = 0
+    add("ragged", torch.randn(B, T, D, generator=g), ds)
+    # zeros inside rows + one all-zero row inside a non-zero batch, non-zero pad value
+    ds = torch.randint(0, 4, (3, 10), generator=g)
+    ds[1] = 0
+    add("zero_row", torch.randn(3, 10, 192, generator=g), ds, pad=-1.5)
+    # whole batch zero: in-place fix-up to ones, T_out = Tmax
+    add("all_zero_batch", torch.randn(2, 7, 256, generator=g), torch.zeros(2, 7, dtype=torch.long))
+    # alpha != 1 (round half to even): appendix 9.6 example plus a random one
+    add("alpha_1p5_small", torch.randn(2, 3, 4, generator=g), torch.tensor([[2, 1, 1], [1, 1, 1]]), alpha=1.5)
+    add("alpha_0p5", torch.randn(3, 11, 384, generator=g), torch.randint(0, 9, (3, 11), generator=g), alpha=0.5)
+    add("alpha_1p5", torch.randn(3, 11, 384, generator=g), torch.randint(0, 9, (3, 11), generator=g), alpha=1.5)
+    # alpha that rounds everything to zero -> fix-up happens on the scaled copy, caller's ds untouched
+    add("alpha_to_zero", torch.randn(2, 5, 16, generator=g), torch.ones(2, 5, dtype=torch.long), alpha=0.25)
+    # odd feature width (no 16-byte rows), Tmax not a multiple of 4
+    add("odd_width", torch.randn(2, 7, 5, generator=g), torch.randint(0, 5, (2, 7), generator=g))
+    add("width_1", torch.randn(2, 6, 1, generator=g), torch.randint(1, 3, (2, 6), generator=g))
+    # single long row
+    add("long_row", torch.randn(1, 300, 64, generator=g), torch.randint(0, 7, (1, 300), generator=g))
+    flat = {}
+    for name, c in cases.items():
+        for k, v in c.items():
+            flat[f"{name}.{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "lr_cases.npz"), **flat)
+    print("lr_cases:", list(cases))
+
+
+def hifigan_small():
+    HiFiGAN, _ = ref_loader.load_hifigan()
+    torch.manual_seed(7)
+    cfg = dict(in_channels=8, out_channels=1, channels=32, global_channels=4, kernel_size=7,
+               upsample_scales=[4, 2], upsample_kernel_sizes=[8, 4], resblock_kernel_sizes=[3, 5],
+               resblock_dilations=[[1, 3], [1, 2]])
+    m = HiFiGAN(**cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    c = torch.randn(3, 8, 37, generator=g)
+    gc = torch.randn(3, 4, 1, generator=g)
+    with torch.no_grad():
+        y = m(c, gc)
+        y_nog = m(c)
+    np.savez_compressed(os.path.join(OUT, "hifigan_small.npz"), c=c.numpy(), g=gc.numpy(), y=y.numpy(),
+                        y_nog=y_nog.numpy(), **sd_to_np(m.state_dict()))
+    # use_additional_convs=False, bias=False, odd upsample scale (output_padding path), no weight norm
+    torch.manual_seed(8)
+    cfg2 = dict(in_channels=6, out_channels=1, channels=16, kernel_size=5, upsample_scales=[3, 2],
+                upsample_kernel_sizes=[6, 4], resblock_kernel_sizes=[3], resblock_dilations=[[1, 2, 3]],
+                use_additional_convs=False, bias=False, use_weight_norm=False)
+    m2 = HiFiGAN(**cfg2).eval()
+    c2 = torch.randn(2, 6, 21, generator=g)
+    with torch.no_grad():
+        y2 = m2(c2)
+    np.savez_compressed(os.path.join(OUT, "hifigan_small2.npz"), c=c2.numpy(), y=y2.numpy(), **sd_to_np(m2.state_dict()))
+    print("hifigan_small:", tuple(y.shape), tuple(y2.shape))
+
+
+def hifigan_v1():
+    HiFiGAN, _ = ref_loader.load_hifigan()
+    torch.manual_seed(1234)  # config/train_config.yaml:1
+    m = HiFiGAN().eval()
+    sd = m.state_dict()
+    g = torch.Generator().manual_seed(0)
+    c = torch.randn(2, 80, 24, generator=g)
+    with torch.no_grad():
+        y = m(c)
+        inf = m.inference(c[0].transpose(0, 1))
+    keys = sorted(sd.keys())
+    sums = np.array([float(sd[k].double().sum()) for k in keys])
+    abss = np.array([float(sd[k].double().abs().sum()) for k in keys])
+    np.savez_compressed(os.path.join(OUT, "hifigan_v1.npz"), c=c.numpy(), y=y.numpy(), inference=inf.numpy(),
+                        keys=np.array(keys), shapes=np.array([str(tuple(sd[k].shape)) for k in keys]),
+                        sums=sums, abs_sums=abss, seed=np.int64(1234))
+    print("hifigan_v1:", tuple(y.shape), len(keys))
+
+
+def vits2_small():
+    Generator, _, _ = ref_loader.load_vits2_generator()
+    g = torch.Generator().manual_seed(2)
+    out = {}
+    for tag, rb, dil in (("rb1", "1", [[1, 3, 5], [1, 2, 4]]), ("rb2", "2", [[1, 3], [1, 2]])):
+        torch.manual_seed(11)
+        import contextlib, io
+        m = Generator(12, resblock=rb, resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=dil,
+                      upsample_rates=[4, 2], upsample_initial_channel=32, upsample_kernel_sizes=[8, 4],
+                      gin_channels=5).eval()
+        x = torch.randn(2, 12, 19, generator=g)
+        gc = torch.randn(2, 5, 1, generator=g)
+        with torch.no_grad():
+            y = m(x, gc)
+        out.update({f"{tag}.x": x.numpy(), f"{tag}.g": gc.numpy(), f"{tag}.y": y.numpy()})
+        out.update(sd_to_np(m.state_dict(), prefix=f"{tag}.sd."))
+    np.savez_compressed(os.path.join(OUT, "vits2_small.npz"), **out)
+    print("vits2_small ok")
+
+
+if __name__ == "__main__":
+    assert ref_loader.reference_available(), "needs /root/reference"
+    lr_cases()
+    hifigan_small()
+    hifigan_v1()
+    vits2_small()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))

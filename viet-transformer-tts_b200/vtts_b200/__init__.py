@@ -1,0 +1,20 @@
+"""vtts_b200 -- B200-native (sm_100a) synthesis hot path for Viet-Transformer-TTS.
+
+Host-side mirror of the reference's module interface for ONE path: LengthRegulator ->
+HiFi-GAN generator.  Everything numeric happens in libvtts_b200.so (hand-written CUDA behind
+the C ABI in include/vtts_b200.h); this package is plumbing: parameter containers with the
+reference's ``state_dict`` keys, ctypes calls, batch sharding across ranks.
+"""
+from . import _lib
+from .dropin import install, uninstall
+from .hifigan import HiFiGAN, ResidualBlock
+from .length_regulator import LengthRegulator
+from .sharding import gather_waveforms, plan_shards, shard_batch
+from .synthesis import Synthesizer
+from .vits2 import Generator, ResBlock1, ResBlock2
+
+__all__ = [
+    "HiFiGAN", "ResidualBlock", "LengthRegulator", "Generator", "ResBlock1", "ResBlock2",
+    "Synthesizer", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall",
+]
+__version__ = "0.1.0"
