@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- synthesized audio seconds per second (inverse RTF) of the hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+Workload (BASELINE.json configs[1]): FastSpeech2 (4-layer, 256-hidden) LengthRegulator +
+HiFi-GAN V1, batch 16 synthetic phoneme sequences per GPU: hidden states (16, 120, 256) fp32,
+integer durations 1..11 inside each utterance's text length (40..120), 0 outside ->
+LengthRegulator -> (acoustic decoder stand-in: first 80 features as the mel) -> HiFi-GAN V1
+-> 22.05 kHz waveform.  Random-init weights drawn with torch.manual_seed(1234).
+
+One "step" = one pass of the hot path over one batch.  `value` counts only VALID audio
+(sum_b mel_len_b * 256 / 22050), not the padded tail of shorter utterances.
+
+Under torchrun (N > 1) every rank runs its own batch (weak scaling, no data-path collective);
+time = max over ranks, value = all ranks' audio / that time.
+
+`--impl reference` times the reference's algorithm on the host CPU instead (rank 0 only):
+the reference is pure Python and cannot travel to the GPU box, so the arm runs the CPU oracle
+port (oracle/restate.py -- the same torch.nn.functional calls the reference modules make) with
+all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "viet-transformer-tts_b200"))
+
+SAMPLE_RATE = 22050
+HOP = 256
+FLOP_PER_FRAME_V1 = 614_105_088  # BASELINE.md section 3 (2*MAC, convs only, in_channels = 80)
+
+
+def make_workload(seed: int, B: int = 16, Ttext: int = 120, D: int = 256):
+    """SURVEY.md section 8d, C2 recipe (LR unit-bench variant: ds = randint(1,12) inside length)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    hs = torch.randn(B, Ttext, D, generator=g)
+    text_len = torch.randint(40, Ttext + 1, (B,), generator=g)
+    text_len[0] = Ttext
+    ds = torch.randint(1, 12, (B, Ttext), generator=g)
+    ds[torch.arange(Ttext)[None, :] >= text_len[:, None]] = 0
+    return hs, ds
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons while the timed region runs (pynvml)."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                try:
+                    phys = int(visible.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_oracle_run(hs, ds, sd_folded, n_utts: int, repeats: int):
+    """Time the CPU oracle port on the first `n_utts` utterances.  Returns (audio_s, seconds/run)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restate
+
+    hs_s, ds_s = hs[:n_utts].clone(), ds[:n_utts].clone()
+    audio = float(ds_s.sum()) * HOP / SAMPLE_RATE
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            frames, _ = restate.lr_expand(hs_s, ds_s.clone())
+            mel = frames[..., :80].transpose(1, 2).contiguous()
+            restate.hifigan_forward(sd_folded, mel)
+            times.append(time.perf_counter() - t0)
+    return audio, times
+
+
+def fold_state_dict(sd):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import restate
+
+    out = {}
+    for k, v in sd.items():
+        if k.endswith(".weight_g"):
+            p = k[: -len(".weight_g")]
+            out[p + ".weight"] = restate.fold_weight_norm(v.detach().cpu(), sd[p + ".weight_v"].detach().cpu())
+        elif k.endswith(".weight_v"):
+            continue
+        else:
+            out[k] = v.detach().cpu()
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    import vtts_b200
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    gen = vtts_b200.HiFiGAN()
+    sd = fold_state_dict(gen.state_dict())
+    hs, ds = make_workload(0)
+    n_utts = args.ref_utts
+    for _ in range(args.warmup):
+        cpu_oracle_run(hs, ds, sd, n_utts, 1)
+    audio, times = cpu_oracle_run(hs, ds, sd, n_utts, args.steps)
+    total = sum(times)
+    value = audio * args.steps / total
+    sample = f"first {n_utts} of 16 utterances per step ({audio:.2f} s audio), fp32, weight-norm pre-folded"
+    line = {
+        "impl": "reference", "metric": "synthesized audio sec/sec (inverse RTF)", "value": value,
+        "unit": "audio_s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: LengthRegulator (16,120,256) + HiFi-GAN V1, 22.05 kHz, batch 16/GPU",
+                   "reference_arm": "CPU oracle port of the reference modules, bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "audio_s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio_s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--ref-utts", type=int, default=2, help="utterances per step for the CPU arms")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    import vtts_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    precision = args.precision or vtts_b200.hifigan.DEFAULT_PRECISION
+    torch.manual_seed(1234)  # config/train_config.yaml:1 -- identical weights on every rank
+    gen = vtts_b200.HiFiGAN()
+    gen.precision = precision
+    gen = gen.to(dev).eval()
+    lr = vtts_b200.LengthRegulator()
+    synth = vtts_b200.Synthesizer(gen, lr)
+
+    hs, ds = make_workload(seed=rank, B=args.batch)
+    hs_pin, ds_pin = hs.pin_memory(), ds.pin_memory()
+    hs_d, ds_d = hs.to(dev), ds.to(dev)
+    valid_frames = int(ds.sum())
+    audio_s = valid_frames * HOP / SAMPLE_RATE
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
+        mel = frames[..., :80].transpose(1, 2)
+        wav = gen(mel)
+        return frames, wav
+
+    def step_generator_only(mel):
+        return gen(mel)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            frames, wav = step_device()
+            synth(hs_pin, ds_pin)
+        torch.cuda.synchronize(dev)
+        T_out = frames.shape[1]
+        padded_frames = frames.shape[0] * T_out
+        launches_per_step = 2 + gen.last_launch_count
+
+        # ---- device-resident timing: K steps, L2 flushed between steps (outside the events) ----
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        with ClockSampler(local) as clocks:
+            for k in range(args.steps):
+                flush.fill_(k & 0xFF)
+                ev[k][0].record()
+                frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
+                mel = frames[..., :80].transpose(1, 2)
+                gev[k][0].record()
+                wav = gen(mel)
+                gev[k][1].record()
+                ev[k][1].record()
+            barrier()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        gen_ms = [a.elapsed_time(b) for a, b in gev]
+        total_ms = sum(step_ms)
+
+        # ---- end-to-end through the public API with host buffers (H2D + D2H inside) -------------
+        e2e_ms = []
+        barrier()
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            wav_h, wav_len_h = synth(hs_pin, ds_pin)  # synchronises before returning
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        barrier()
+        e2e_total = sum(e2e_ms)
+
+    t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device=dev)
+    a = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    total_ms_all, e2e_ms_all = t.tolist()
+    audio_all = float(a.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        gen_avg_ms = sum(gen_ms) / len(gen_ms)
+        flops = padded_frames * FLOP_PER_FRAME_V1
+        achieved = flops / (gen_avg_ms * 1e-3) / 1e12
+        value = audio_all * args.steps / (total_ms_all * 1e-3)
+        line = {
+            "metric": "synthesized audio sec/sec (inverse RTF)", "value": value, "unit": "audio_s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: LengthRegulator (16,120,256) + HiFi-GAN V1, 22.05 kHz, batch 16/GPU",
+                "precision": precision, "batch_per_gpu": args.batch, "padded_mel_frames": padded_frames,
+                "valid_mel_frames": valid_frames, "l2": "256 MiB flush buffer written between timed steps; "
+                "per-step activation working set also exceeds the 126 MB L2",
+                "value_counts": "valid (unpadded) audio only",
+            },
+            "clocks": clocks.summary(),
+            "e2e": {"value": audio_all * args.steps / (e2e_ms_all * 1e-3), "unit": "audio_s/s",
+                    "h2d_bytes_per_step": hs.numel() * 4 + ds.numel() * 8,
+                    "d2h_bytes_per_step": int(wav.numel()) * 4 + ds.shape[0] * 8,
+                    "ms_per_step": e2e_ms_all / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tc_peak, "traffic": None,
+                         "kernel": "generator conv kernels (all launches of one forward)",
+                         "flops_per_launch_set": flops, "ms": gen_avg_ms, "peak_source": peak_src},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sd = fold_state_dict(gen.state_dict())
+            cpu_oracle_run(hs, ds, sd, 1, 1)  # warm-up
+            caudio, ctimes = cpu_oracle_run(hs, ds, sd, args.ref_utts, 3)
+            ctimes.sort()
+            line["cpu_baseline"] = {
+                "value": caudio / ctimes[len(ctimes) // 2], "unit": "audio_s/s", "cores": cores, "kind": "port",
+                "sample": f"first {args.ref_utts} of {args.batch} utterances ({caudio:.2f} s audio), median of 3, "
+                          "CPU oracle port (torch fp32, weight-norm pre-folded)",
+            }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

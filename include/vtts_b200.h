@@ -157,6 +157,12 @@ int vtts_dbg_conv1d_fp32(const float *x, const float *w, const float *bias, cons
 int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float *d, int M, int N, int K,
                        int a_rows_total, int row_shift, int variant, vtts_stream_t stream);
 
+/* One Conv1d layer through the tcgen05 kernel (bf16 operands, fp32 accumulate), channels-first
+ * fp32 in/out: y = conv(bf16(lrelu_in(x))) + bias [+ res]; y_act (optional) = bf16(lrelu_out(y)). */
+int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const float *res, float *y,
+                       float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
+                       float slope_in, float slope_out, vtts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

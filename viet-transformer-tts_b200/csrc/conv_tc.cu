@@ -1,16 +1,817 @@
-// conv_tc.cu -- tcgen05 path (placeholder until the implicit-GEMM kernels land).
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for the HiFi-GAN generator.
+//
+// Every convolution of the generator (generator.py:132-156, layers.py:93-97) is lowered to
+//     D[n, i] = sum_j sum_ci  Wp[j][n][ci] * X[i + off_j][ci]          (bf16 x bf16 -> fp32)
+// with n = output row (out channel, or (phase, out channel) for the polyphase transposed conv,
+// SURVEY.md appendix 9.1), i = time position, off_j = tap_off0 + j * tap_step.
+//
+// Data layout in HBM: activations are channels-last (B, L, C): the bf16 operand copy already has
+// the next layer's LeakyReLU applied; the residual stream stays fp32.  Weights are packed
+// [tap][n_pad][ci_pad] bf16 (K-major rows).
+//
+// One CTA = 128 output rows (UMMA M, TMEM lanes) x TN=256 time positions (UMMA N, TMEM
+// columns).  The weight tile is the A operand, the activation tile the B operand.  The
+// activation tile is loaded ONCE per 64-channel chunk with its halo (TN + (k-1)*d rows) and
+// every tap reads it through a row-shifted shared-memory descriptor, so a k-tap conv moves the
+// activations HBM/L2 -> SMEM once instead of k times.  Warp roles: activation TMA producer,
+// weight TMA producer, MMA issuer (one elected thread), and epilogue warps that read the
+// accumulator with tcgen05.ld (thread = output channel, registers = consecutive time steps, so
+// a warp's global accesses are 32 consecutive channels of one time step = one 128-byte line)
+// and fuse bias + residual + MRF accumulate/mean + LeakyReLU + bf16 re-quantisation.
 #include "generator.cuh"
+#include "tc_common.cuh"
+
+#include <map>
+#include <mutex>
+#include <string.h>
+
 namespace vtts {
-int tc_pack_layer(VttsGen *, int, cudaStream_t) { return VTTS_OK; }
-int tc_workspace_bytes(const VttsGen *, int, int, size_t *) {
-    return set_error(VTTS_E_UNSUPPORTED, "bf16 tcgen05 path not built");
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
 }
-int tc_forward(VttsGen *, const float *, const float *, float *, int, int, void *, size_t, int, float *, cudaStream_t) {
-    return set_error(VTTS_E_UNSUPPORTED, "bf16 tcgen05 path not built");
+
+int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
+                   const uint64_t *strides_bytes, const uint32_t *box, int swizzle_bytes) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return set_error(VTTS_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];  // strides of dims 1..rank-1
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr,
+                     bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(VTTS_E_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u",
+                         (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                         (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0,
+                         rank > 2 ? box[2] : 0);
+    return VTTS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TN = 256;          // time positions per CTA (UMMA N, TMEM columns)
+constexpr int TM = 128;          // output rows per CTA (UMMA M, TMEM lanes)
+constexpr int HALO_MAX = 64;     // (k-1)*d <= 64
+constexpr int ACT_ROWS = TN + HALO_MAX;
+constexpr int BOX_ROWS = 64;     // activation TMA box height
+constexpr int PRODUCER_WARPS = 3;  // act producer, weight producer, MMA issuer
+
+struct TcConvParams {
+    // epilogue tensors (channels-last)
+    const float *bias;      // (n_total) or null  -- indexed by output row n
+    const float *bias_b;    // (B, n_total) or null
+    const float *res;       // (B, L_out, cout) fp32 or null
+    float *out_x;           // (B, L_out, cout) fp32 or null
+    __nv_bfloat16 *out_a;   // (B, L_out, out_a_ld) bf16 or null
+    int out_a_ld;
+    float slope_out;        // LeakyReLU slope applied to the bf16 copy (1 = identity)
+    int accumulate;         // out_x = out_x_old + value
+    float divide_by;        // > 0: value /= divide_by
+    // geometry
+    int n_total;            // valid output rows (cout * phases)
+    int cout;               // channels per phase
+    int L_out;
+    int n_pos;              // time positions (GEMM N extent)
+    int out_stride, out_off0;  // t_out = i * out_stride + out_off0 + phase
+    int chunks;             // K chunks (ci_pad / chunk_elems)
+    int taps, tap_off0, tap_step;
+    int act_stages, w_stages;
+};
+
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = (PRODUCER_WARPS + EPI_WARPS) * 32;
+
+template <int ROWB>  // bytes per operand row: 128 (64 channels, SW128) or 64 (32 channels, SW64)
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
+               const TcConvParams p) {
+    constexpr int CH = ROWB / 2;                 // bf16 channels per chunk
+    constexpr int KSTEPS = CH / 16;              // UMMA K = 16
+    constexpr int ACT_BYTES = ACT_ROWS * ROWB;
+    constexpr int W_BYTES = TM * ROWB;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // swizzle atoms need 1024-byte aligned stage bases; every stage size is a multiple of 1024
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("vtts: dynamic shared memory base not 1024-byte aligned\n");
+        __trap();
+    }
+    uint8_t *s_act = smem;
+    uint8_t *s_w = smem + (size_t)p.act_stages * ACT_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + (size_t)p.w_stages * W_BYTES);
+    uint64_t *act_full = bars, *act_empty = bars + p.act_stages;
+    uint64_t *w_full = bars + 2 * p.act_stages, *w_empty = w_full + p.w_stages;
+    uint64_t *acc_full = w_empty + p.w_stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * TN;       // first time position of this tile
+    const int n0 = blockIdx.y * TM;       // first output row
+    const int b = blockIdx.z;
+    const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
+    const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
+    const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
+    const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.act_stages; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
+        for (int s = 0; s < p.w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {  // MMA warp owns the TMEM allocation
+        tmem_alloc(tmem_slot, TN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_act);
+            for (int c = 0; c < p.chunks; ++c) {
+                const int s = c % p.act_stages;
+                const uint32_t ph = (uint32_t)(c / p.act_stages) & 1u;
+                mbar_wait(&act_empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
+                for (int bx = 0; bx < nbox; ++bx)
+                    tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s],
+                                c * CH, i0 + min_off + bx * BOX_ROWS, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== weight producer: one 128-row tile per (chunk, tap) =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_w);
+            int it = 0;
+            for (int c = 0; c < p.chunks; ++c)
+                for (int j = 0; j < p.taps; ++j, ++it) {
+                    const int s = it % p.w_stages;
+                    const uint32_t ph = (uint32_t)(it / p.w_stages) & 1u;
+                    mbar_wait(&w_empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&w_full[s], (uint32_t)W_BYTES);
+                    tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
+                }
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TM, TN);
+            int it = 0;
+            for (int c = 0; c < p.chunks; ++c) {
+                const int sa = c % p.act_stages;
+                mbar_wait(&act_full[sa], (uint32_t)(c / p.act_stages) & 1u);
+                const uint32_t act_base = smem_u32(s_act + (size_t)sa * ACT_BYTES);
+                for (int j = 0; j < p.taps; ++j, ++it) {
+                    const int sw = it % p.w_stages;
+                    mbar_wait(&w_full[sw], (uint32_t)(it / p.w_stages) & 1u);
+                    tc_fence_after();
+                    const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
+                    const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        const uint64_t adesc = make_smem_desc(w_base + ks * 32, ROWB, 0);
+                        const uint64_t bdesc = make_smem_desc(act_base + row * ROWB + ks * 32, ROWB, 0);
+                        umma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)((c | j | ks) != 0));
+                    }
+                    umma_commit(&w_empty[sw]);   // weight stage reusable once these MMAs retire
+                }
+                umma_commit(&act_empty[sa]);     // activation stage reusable
+            }
+            umma_commit(acc_full);               // accumulator complete -> epilogue
+        }
+    } else {
+        // ===== epilogue warps: thread = output row (channel), registers = time positions =====
+        const int ew = warp - PRODUCER_WARPS;
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+        const int rows_valid = p.n_total - n0;              // valid rows in this CTA
+        const int quarters_used = rows_valid >= TM ? 4 : (rows_valid + 31) / 32;
+        if (quarter < quarters_used) {
+            // the two warps sharing a quarter split the TN columns
+            constexpr int SHARERS = EPI_WARPS / 4;
+            constexpr int COLS_PER = TN / SHARERS;
+            const int col_lo = (ew / 4) * COLS_PER;
+            const int n = n0 + quarter * 32 + lane;         // global output row of this thread
+            const bool row_ok = n < p.n_total;
+            const int phase = row_ok ? n / p.cout : 0;
+            const int co = row_ok ? n - phase * p.cout : 0;
+            float bias = 0.f;
+            if (row_ok && p.bias) bias = __ldg(p.bias + n);
+            if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.n_total + n);
+            const size_t step = (size_t)p.out_stride * p.cout;       // elements between time positions
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            for (int cg = 0; cg < COLS_PER; cg += 32) {
+                const int col = col_lo + cg;
+                if (i0 + col >= p.n_pos) break;             // warp-uniform: nothing valid beyond
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int ibase = i0 + col + half * 16;
+                    const long long t_first = (long long)ibase * p.out_stride + p.out_off0 + phase;
+                    // offset of element e: off0 + e * step   (only dereferenced when valid)
+                    const long long off0 = ((long long)b * p.L_out + t_first) * p.cout + co;
+                    uint32_t okmask = 0;
+                    float rr[16], aa[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const long long t = t_first + (long long)e * p.out_stride;
+                        const bool ok = row_ok && (ibase + e) < p.n_pos && t >= 0 && t < p.L_out;
+                        okmask |= (ok ? 1u : 0u) << e;
+                        rr[e] = (ok && p.res) ? __ldg(p.res + off0 + (long long)e * (long long)step) : 0.f;
+                        aa[e] = (ok && p.accumulate) ? p.out_x[off0 + (long long)e * (long long)step] : 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        if (okmask & (1u << e)) {
+                            const long long off = off0 + (long long)e * (long long)step;
+                            float val = __uint_as_float(v[half * 16 + e]) + bias;
+                            if (p.res) val = val + rr[e];
+                            if (p.accumulate) val = aa[e] + val;
+                            if (p.divide_by > 0.f) val = __fdiv_rn(val, p.divide_by);
+                            if (p.out_x) p.out_x[off] = val;
+                            if (p.out_a) {
+                                const long long rowi = (off - co) / p.cout;
+                                p.out_a[rowi * p.out_a_ld + co] = __float2bfloat16(lrelu(val, p.slope_out));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TN);
+}
+
+struct TcLaunch {
+    CUtensorMap tm_act, tm_w;
+    TcConvParams p;
+    int rowb;
+    dim3 grid;
+    int threads;
+    size_t smem;
+};
+
+static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
+    return (size_t)act_stages * ACT_ROWS * rowb + (size_t)w_stages * TM * rowb +
+           (size_t)(2 * act_stages + 2 * w_stages + 1) * 8 + 16;
+}
+
+static int tc_launch(const TcLaunch &L, cudaStream_t st) {
+    if (L.rowb == 128) {
+        static bool attr128 = false;
+        if (!attr128) {
+            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr128 = true;
+        }
+        conv_tc_kernel<128><<<L.grid, L.threads, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
+    } else {
+        static bool attr64 = false;
+        if (!attr64) {
+            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr64 = true;
+        }
+        conv_tc_kernel<64><<<L.grid, L.threads, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
+    }
+    VTTS_CHECK_LAUNCH();
+    return VTTS_OK;
+}
+
+// Build a launch for one layer.  act: (B, L_in, ci_pad) bf16; w: [taps][n_pad][ci_pad] bf16.
+static int tc_prepare(TcLaunch &L, const __nv_bfloat16 *act, int B, int L_in, int ci_pad,
+                      const __nv_bfloat16 *w, int n_pad, TcConvParams p) {
+    const int rowb = (ci_pad % 64 == 0) ? 128 : 64;
+    const int ch = rowb / 2;
+    if (ci_pad % ch != 0) return set_error(VTTS_E_UNSUPPORTED, "tc: ci_pad %d not a multiple of %d", ci_pad, ch);
+    const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
+    const int span = last_off > p.tap_off0 ? last_off - p.tap_off0 : p.tap_off0 - last_off;
+    if (span > HALO_MAX) return set_error(VTTS_E_UNSUPPORTED, "tc: tap span %d > %d", span, HALO_MAX);
+    L.rowb = rowb;
+    p.chunks = ci_pad / ch;
+    // pipeline depth: single-chunk layers keep one activation stage and deeper weight stages
+    if (p.chunks == 1) { p.act_stages = 1; p.w_stages = 4; }
+    else { p.act_stages = 2; p.w_stages = 2; }
+    if (p.w_stages > p.chunks * p.taps) p.w_stages = p.chunks * p.taps;
+    L.p = p;
+    L.threads = TC_THREADS;
+    L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
+    L.grid = dim3((unsigned)ceil_div(p.n_pos, TN), (unsigned)(n_pad / TM), (unsigned)B);
+    {
+        uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)L_in, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)L_in};
+        uint32_t box[3] = {(uint32_t)ch, BOX_ROWS, 1};
+        int rc = make_tmap_bf16(&L.tm_act, act, 3, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)n_pad, (uint64_t)p.taps};
+        uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)n_pad};
+        uint32_t box[3] = {(uint32_t)ch, TM, 1};
+        int rc = make_tmap_bf16(&L.tm_w, w, 3, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    return VTTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 reference layout -> bf16 [tap][n_pad][ci_pad]
+// ---------------------------------------------------------------------------------------------
+// Conv1d (cout,cin,k): n = co, tap j = kernel index.
+// ConvTranspose1d (cin,cout,k), stride s: n = q*cout + co, tap j reads x[i0 - j], weight index q + j*s.
+__global__ void pack_tc_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int kind, int cin,
+                               int cout, int k, int s, int taps, int n_pad, int ci_pad) {
+    const size_t total = (size_t)taps * n_pad * ci_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(idx % ci_pad);
+        const size_t rest = idx / ci_pad;
+        const int n = (int)(rest % n_pad), j = (int)(rest / n_pad);
+        float v = 0.f;
+        if (ci < cin) {
+            if (kind == 0) {
+                if (n < cout) v = w[((size_t)n * cin + ci) * k + j];
+            } else {
+                const int q = n / cout, co = n - q * cout;
+                if (q < s) v = w[((size_t)ci * cout + co) * k + q + j * s];
+            }
+        }
+        out[idx] = __float2bfloat16(v);
+    }
+}
+
+// conv_post on channels-last fp32 input: y[b, 0, t] = tanh(bias + sum_k sum_ci w[ci,k] * lrelu(x[b, t+k-h, ci]))
+// (generator.py:108-120; kept in fp32 -- SURVEY.md section 0: output_conv dominates the bf16 error).
+// HBM-bound: reads C*4 bytes per sample once (neighbouring taps hit L1), writes 4.
+template <int C>
+__global__ void __launch_bounds__(256)
+conv_post_cl_kernel(const float *__restrict__ x, const float *__restrict__ w /* [k][C] */, const float *__restrict__ bias,
+                    float *__restrict__ y, int L, int ksize, float slope, int out_channels, int oc) {
+    extern __shared__ float s_tile[];  // [(256 + ksize - 1)][C + 1]
+    const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;
+    const int rows = 256 + ksize - 1;
+    const float *xb = x + (size_t)b * L * C;
+    for (int idx = threadIdx.x; idx < rows * C; idx += 256) {
+        const int r = idx / C, c = idx - r * C;
+        const int t = t0 - h + r;
+        s_tile[r * (C + 1) + c] = (t >= 0 && t < L) ? lrelu(__ldg(xb + (size_t)t * C + c), slope) : 0.f;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= L) return;
+    float acc = 0.f;
+    for (int k = 0; k < ksize; ++k) {
+        const float *row = s_tile + (threadIdx.x + k) * (C + 1);
+        const float *wk = w + k * C;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(wk + c), row[c], acc);
+    }
+    if (bias) acc += __ldg(bias + oc);
+    y[((size_t)b * out_channels + oc) * L + t] = tanhf(acc);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// handle integration
+// ---------------------------------------------------------------------------------------------
+using namespace tc;
+
+static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+static int ci_pad_of(int cin) { return cin % 64 == 0 ? cin : (cin == 32 ? 32 : pad_to(cin, 64)); }
+
+// output conv weights (cout, cin, k) -> [oc][k][ci] fp32 for conv_post_cl_kernel
+__global__ void pack_post_kernel(const float *__restrict__ w, float *__restrict__ out, int cout, int cin, int k) {
+    const int n = cout * cin * k;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int ci = idx % cin, kk = (idx / cin) % k, oc = idx / (cin * k);
+        out[idx] = w[((size_t)oc * cin + ci) * k + kk];
+    }
+}
+
+int tc_pack_layer(VttsGen *h, int layer, cudaStream_t st) {
+    Layer &l = h->layers[layer];
+    const int cin = l.info.cin, cout = l.info.cout, k = l.info.ksize;
+    const bool transposed = l.info.kind == 1;
+    const int s = transposed ? l.stride : 1;
+    const int taps = transposed ? k / s : k;
+    l.ci_pad = ci_pad_of(cin);
+    l.n_total = transposed ? s * cout : cout;
+    const int n_pad = pad_to(l.n_total, TM);
+    const size_t n = (size_t)taps * n_pad * l.ci_pad;
+    if (!l.w_bf16) VTTS_CHECK_CUDA(cudaMalloc(&l.w_bf16, n * sizeof(__nv_bfloat16)));
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 8192) blocks = 8192;
+    pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w_bf16, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad);
+    VTTS_CHECK_LAUNCH();
+    if (layer == h->idx_post) {
+        if (!l.w_aux) VTTS_CHECK_CUDA(cudaMalloc(&l.w_aux, (size_t)cin * cout * k * sizeof(float)));
+        pack_post_kernel<<<ceil_div(cin * cout * k, 256), 256, 0, st>>>(l.w_fold, l.w_aux, cout, cin, k);
+        VTTS_CHECK_LAUNCH();
+    }
+    return VTTS_OK;
+}
+
 void tc_destroy(VttsGen *) {}
-int tc_supported(const VttsGen *, char *, size_t) { return 0; }
+
+
+
+int tc_supported(const VttsGen *h, char *why, size_t why_len) {
+    const VttsGenConfig &c = h->cfg;
+    auto fail = [&](const char *msg) { if (why) snprintf(why, why_len, "%s", msg); return 0; };
+    int ch = c.channels;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        ch /= 2;
+        if (ch != 32 && ch % 64 != 0) return fail("bf16 path needs every stage width to be 32 or a multiple of 64 channels");
+        if ((c.upsample_kernel_sizes[i] / c.upsample_scales[i]) - 1 > HALO_MAX) return fail("upsample taps too wide");
+    }
+    if (c.channels % 64 != 0) return fail("bf16 path needs channels to be a multiple of 64");
+    for (int j = 0; j < c.num_blocks; ++j)
+        for (int m = 0; m < c.num_dilations[j]; ++m)
+            if ((c.resblock_kernel_sizes[j] - 1) * c.resblock_dilations[j][m] > HALO_MAX)
+                return fail("bf16 path needs (kernel-1)*dilation <= 64");
+    if (c.kernel_size - 1 > HALO_MAX) return fail("input conv too wide");
+    const int cl = c.channels >> c.num_upsamples;
+    if (cl != 32 && cl != 64 && cl != 128) return fail("bf16 path: last stage width must be 32/64/128 for the fp32 output conv");
+    return 1;
+}
+
+namespace {
+struct TcPlan {
+    std::vector<int> C, L;
+    size_t max_rows_c = 0;  // max over stages of L*C (per batch)
+};
+static int convT_len(int L, int s, int k, int p, int op) { return (L - 1) * s - 2 * p + k + op; }
+static TcPlan tc_plan(const VttsGen *h, int T) {
+    TcPlan p;
+    int ch = h->cfg.channels, L = T;
+    p.max_rows_c = (size_t)ch * L;
+    for (int i = 0; i < h->cfg.num_upsamples; ++i) {
+        const Layer &u = h->layers[h->idx_up[i]];
+        L = convT_len(L, u.stride, u.info.ksize, u.padding, u.output_padding);
+        ch /= 2;
+        p.C.push_back(ch); p.L.push_back(L);
+        size_t e = (size_t)ch * (size_t)(L > 0 ? L : 0);
+        if (e > p.max_rows_c) p.max_rows_c = e;
+    }
+    return p;
+}
+struct TcBuffers {
+    __nv_bfloat16 *a_in;   // input operand (B, T, ci_pad)
+    __nv_bfloat16 *a_u, *a_p, *a_q, *a_t, *a_c;  // bf16 operand copies (max stage size)
+    float *x_u, *x_p, *x_q, *x_cs;                // fp32 residual stream
+    float *gb;                                    // (B, channels) global conditioning bias
+    float *tmp;                                   // fp32 staging for dumps / conditioning input
+    size_t total;
+};
+static TcBuffers tc_carve(const VttsGen *h, int B, int T, void *ws) {
+    TcPlan pl = tc_plan(h, T);
+    const size_t elems = (size_t)B * pl.max_rows_c;
+    const size_t in_pad = (size_t)B * T * ci_pad_of(h->cfg.in_channels);
+    char *p = (char *)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes, 1024); return r; };
+    TcBuffers b{};
+    b.a_in = (__nv_bfloat16 *)take(in_pad * 2);
+    b.a_u = (__nv_bfloat16 *)take(elems * 2);
+    b.a_p = (__nv_bfloat16 *)take(elems * 2);
+    b.a_q = (__nv_bfloat16 *)take(elems * 2);
+    b.a_t = (__nv_bfloat16 *)take(elems * 2);
+    b.a_c = (__nv_bfloat16 *)take(elems * 2);
+    b.x_u = (float *)take(elems * 4);
+    b.x_p = (float *)take(elems * 4);
+    b.x_q = (float *)take(elems * 4);
+    b.x_cs = (float *)take(elems * 4);
+    b.gb = (float *)take((size_t)B * h->cfg.channels * 4);
+    b.tmp = (float *)take(elems * 4);
+    b.total = off;
+    return b;
+}
+}  // namespace
+
+int tc_workspace_bytes(const VttsGen *h, int B, int T, size_t *bytes) {
+    char why[128];
+    if (!tc_supported(h, why, sizeof(why))) return set_error(VTTS_E_UNSUPPORTED, "%s", why);
+    *bytes = tc_carve(h, B, T, nullptr).total;
+    return VTTS_OK;
+}
+
+namespace {
+// one conv layer on the tensor cores
+static int run_conv(VttsGen *h, const Layer &l, const __nv_bfloat16 *act, int B, int L_in, int L_out, TcConvParams p,
+                    cudaStream_t st) {
+    const bool transposed = l.info.kind == 1;
+    const int s = transposed ? l.stride : 1;
+    p.bias = l.has_bias ? l.bias : nullptr;
+    p.n_total = l.n_total;
+    p.cout = l.info.cout;
+    p.L_out = L_out;
+    if (transposed) {
+        p.taps = l.info.ksize / s; p.tap_off0 = 0; p.tap_step = -1;
+        p.out_stride = s; p.out_off0 = -l.padding; p.n_pos = L_in + p.taps - 1;
+    } else {
+        p.taps = l.info.ksize; p.tap_off0 = -(l.info.ksize - 1) / 2 * l.info.dilation; p.tap_step = l.info.dilation;
+        p.out_stride = 1; p.out_off0 = 0; p.n_pos = L_in;
+    }
+    TcLaunch L;
+    int rc = tc_prepare(L, act, B, L_in, l.ci_pad, l.w_bf16, pad_to(l.n_total, TM), p);
+    if (rc) return rc;
+    if ((rc = tc_launch(L, st))) return rc;
+    h->launch_count++;
+    return VTTS_OK;
+}
+}  // namespace
+
+int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, int T, void *workspace,
+               size_t workspace_bytes, int dump_stage, float *dump_out, cudaStream_t st) {
+    const VttsGenConfig &cfg = h->cfg;
+    char why[128];
+    if (!tc_supported(h, why, sizeof(why))) return set_error(VTTS_E_UNSUPPORTED, "%s", why);
+    TcBuffers bf = tc_carve(h, B, T, workspace);
+    if (workspace_bytes < bf.total) return set_error(VTTS_E_WORKSPACE, "vtts_gen_forward: workspace %zu < %zu", workspace_bytes, bf.total);
+    TcPlan plan = tc_plan(h, T);
+    int rc;
+    auto dump_f32 = [&](int id, const float *src_cl, int C, int L) -> int {
+        if (dump_stage != id || !dump_out) return VTTS_OK;
+        h->launch_count++;
+        return launch_cl_to_cf_f32(src_cl, dump_out, B, C, L, st);
+    };
+
+    // global conditioning bias (tiny 1x1 conv, fp32 CUDA cores)
+    const float *bias_b = nullptr;
+    if (g) {
+        VTTS_REQUIRE(h->idx_global >= 0, "vtts_gen_forward: g given but global_channels <= 0");
+        const Layer &gl = h->layers[h->idx_global];
+        ConvFp32Params p{};
+        p.x = g; p.w = gl.w_f32; p.bias = gl.has_bias ? gl.bias : nullptr; p.y = bf.gb;
+        p.B = B; p.cin = gl.info.cin; p.cout = gl.info.cout; p.L_in = 1; p.L_out = 1; p.taps = 1;
+        p.tap_off0 = 0; p.tap_step = 1; p.phases = 1; p.out_stride = 1; p.out_off0 = 0; p.n_pos = 1; p.slope_in = 1.f;
+        if ((rc = launch_conv_fp32(p, st))) return rc;
+        h->launch_count++;
+        bias_b = bf.gb;
+    }
+    // input layout change: (B, Cin, T) fp32 -> (B, T, ci_pad) bf16
+    const Layer &pre = h->layers[h->idx_pre];
+    if ((rc = launch_cf_to_cl_bf16(c, bf.a_in, B, cfg.in_channels, T, pre.ci_pad, 1.f, st))) return rc;
+    h->launch_count++;
+    {   // input_conv -> bf16 LeakyReLU'd operand for upsample 0 (fp32 copy only when dumped)
+        TcConvParams p{};
+        p.bias_b = bias_b;
+        p.out_a = bf.a_c; p.out_a_ld = cfg.channels; p.slope_out = cfg.lrelu_slope;
+        p.out_x = (dump_stage == 0) ? bf.x_cs : nullptr;
+        if ((rc = run_conv(h, pre, bf.a_in, B, T, T, p, st))) return rc;
+        if ((rc = dump_f32(0, bf.x_cs, cfg.channels, T))) return rc;
+    }
+    const __nv_bfloat16 *cur_a = bf.a_c;
+    int L = T;
+    for (int i = 0; i < cfg.num_upsamples; ++i) {
+        const Layer &u = h->layers[h->idx_up[i]];
+        const int Lo = plan.L[i], C = plan.C[i];
+        VTTS_REQUIRE(Lo > 0, "vtts_gen_forward: stage %d output length %d <= 0", i, Lo);
+        {   // upsample: fp32 residual stream x_u + bf16 operand a_u = lrelu(x_u)
+            TcConvParams p{};
+            p.out_x = bf.x_u; p.out_a = bf.a_u; p.out_a_ld = C; p.slope_out = cfg.lrelu_slope;
+            if ((rc = run_conv(h, u, cur_a, B, L, Lo, p, st))) return rc;
+            if ((rc = dump_f32(2 * i + 1, bf.x_u, C, Lo))) return rc;
+        }
+        const bool last_stage = (i == cfg.num_upsamples - 1);
+        for (int j = 0; j < cfg.num_blocks; ++j) {
+            const float *yx = bf.x_u;
+            const __nv_bfloat16 *ya = bf.a_u;
+            const int nu = cfg.num_dilations[j];
+            for (int m = 0; m < nu; ++m) {
+                const bool last = (m == nu - 1);
+                float *nx = last ? bf.x_cs : ((m & 1) ? bf.x_q : bf.x_p);
+                __nv_bfloat16 *na = (m & 1) ? bf.a_q : bf.a_p;
+                const Layer &l1 = h->layers[h->idx_c1[i][j][m]];
+                const Layer *fin = &l1;
+                const __nv_bfloat16 *fin_in = ya;
+                if (cfg.use_additional_convs) {
+                    TcConvParams p1{};  // xt = conv1(lrelu(x)); only its LeakyReLU'd bf16 copy is needed
+                    p1.out_a = bf.a_t; p1.out_a_ld = C; p1.slope_out = cfg.lrelu_slope;
+                    if ((rc = run_conv(h, l1, ya, B, Lo, Lo, p1, st))) return rc;
+                    fin = &h->layers[h->idx_c2[i][j][m]];
+                    fin_in = bf.a_t;
+                }
+                TcConvParams p2{};
+                p2.res = yx;               // x = xt + x (layers.py:97)
+                p2.out_x = nx;
+                if (last) {                // cs += block(c); c = cs / num_blocks (generator.py:150-153)
+                    p2.accumulate = (j > 0);
+                    if (j == cfg.num_blocks - 1) {
+                        p2.divide_by = (float)cfg.num_blocks;
+                        if (!last_stage) {  // next consumer: LeakyReLU + upsample
+                            p2.out_a = bf.a_c; p2.out_a_ld = C; p2.slope_out = cfg.lrelu_slope;
+                        }
+                    }
+                } else {
+                    p2.out_a = na; p2.out_a_ld = C; p2.slope_out = cfg.lrelu_slope;
+                }
+                if ((rc = run_conv(h, *fin, fin_in, B, Lo, Lo, p2, st))) return rc;
+                yx = nx; ya = na;
+            }
+        }
+        if ((rc = dump_f32(2 * i + 2, bf.x_cs, C, Lo))) return rc;
+        cur_a = bf.a_c;
+        L = Lo;
+    }
+    {   // output_conv in fp32 on the fp32 MRF mean (channels-last), + tanh
+        const Layer &post = h->layers[h->idx_post];
+        const int C = post.info.cin, k = post.info.ksize;
+        const float *wt = post.w_aux;  // [oc][k][ci], packed at load time
+        dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
+        const size_t smem = (size_t)(256 + k - 1) * (C + 1) * sizeof(float);
+        for (int oc = 0; oc < post.info.cout; ++oc) {
+            const float *w_oc = wt + (size_t)oc * k * C;
+            const float *bias = post.has_bias ? post.bias : nullptr;
+#define VTTS_POST(CC)                                                                                         \
+    do {                                                                                                      \
+        if (smem > 48 * 1024)                                                                                 \
+            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_post_cl_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv_post_cl_kernel<CC><<<grid, 256, smem, st>>>(bf.x_cs, w_oc, bias, wav, L, k, cfg.final_lrelu_slope, post.info.cout, oc); \
+    } while (0)
+            if (C == 32) VTTS_POST(32);
+            else if (C == 64) VTTS_POST(64);
+            else if (C == 128) VTTS_POST(128);
+            else return set_error(VTTS_E_UNSUPPORTED, "conv_post: %d input channels", C);
+#undef VTTS_POST
+            VTTS_CHECK_LAUNCH();
+            h->launch_count++;
+        }
+    }
+    return VTTS_OK;
+}
+
 }  // namespace vtts
-extern "C" int vtts_dbg_umma_gemm(const void *, const void *, float *, int, int, int, int, int, int, vtts_stream_t) {
-    return vtts::set_error(VTTS_E_UNSUPPORTED, "umma probe not built");
+
+// ---------------------------------------------------------------------------------------------
+// test hooks
+// ---------------------------------------------------------------------------------------------
+using namespace vtts;
+using namespace vtts::tc;
+
+namespace vtts {
+namespace probe {
+using namespace vtts::tc;
+// Minimal single-CTA GEMM used to pin descriptor semantics on real hardware:
+// D[m, n] = sum_k A[m, k] * B[n + row_shift, k];  M = 128 (TMEM lanes), N columns.
+template <int ROWB>
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, float *d,
+                  int N, int kblocks, int b_rows, int row_shift, int variant) {
+    constexpr int CH = ROWB / 2;
+    constexpr int KSTEPS = CH / 16;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *s_a = smem;                       // 128 rows
+    uint8_t *s_b = smem + 128 * ROWB;          // b_rows rows (multiple of 64)
+    uint64_t *bar_ld = reinterpret_cast<uint64_t *>(s_b + (size_t)b_rows * ROWB);
+    uint64_t *bar_mma = bar_ld + 1;
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar_ld, 1); mbar_init(bar_mma, 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(slot, 256); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_arrive_expect_tx(bar_ld, (uint32_t)((128 + b_rows) * ROWB));
+            tma_load_2d(s_a, &tm_a, bar_ld, kb * CH, 0);
+            tma_load_2d(s_a + 64 * ROWB, &tm_a, bar_ld, kb * CH, 64);
+            for (int r = 0; r < b_rows; r += 64) tma_load_2d(s_b + (size_t)r * ROWB, &tm_b, bar_ld, kb * CH, r);
+            mbar_wait(bar_ld, (uint32_t)kb & 1u);
+            tc_fence_after();
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint32_t a_addr = smem_u32(s_a) + ks * 32;
+                const uint32_t b_addr = smem_u32(s_b) + row_shift * ROWB + ks * 32;
+                const uint32_t bo = (variant & 1) ? ((b_addr >> 7) & 7u) : 0u;
+                umma_bf16(tmem, make_smem_desc(a_addr, ROWB, 0), make_smem_desc(b_addr, ROWB, bo), idesc,
+                          (uint32_t)((kb | ks) != 0));
+            }
+            umma_commit(bar_mma);
+            mbar_wait(bar_mma, (uint32_t)kb & 1u);
+        }
+    }
+    __syncthreads();
+    tc_fence_after();
+    for (int col = 0; col < N; col += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
+        tmem_ld_wait();
+        const int m = warp * 32 + lane;
+        for (int e = 0; e < 32; ++e) d[(size_t)m * N + col + e] = __uint_as_float(v[e]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace probe
+}  // namespace vtts
+using namespace vtts::probe;
+
+extern "C" int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float *d, int M, int N, int K,
+                                  int b_rows_total, int row_shift, int variant, vtts_stream_t stream) {
+    VTTS_REQUIRE(a_bf16 && b_bf16 && d, "vtts_dbg_umma_gemm: null pointer");
+    VTTS_REQUIRE(M == 128, "vtts_dbg_umma_gemm: M must be 128");
+    VTTS_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256, "vtts_dbg_umma_gemm: N must be a multiple of 32 in [32,256]");
+    const int rowb = (variant & 2) ? 64 : 128;
+    const int ch = rowb / 2;
+    VTTS_REQUIRE(K % ch == 0 && K > 0, "vtts_dbg_umma_gemm: K must be a multiple of %d", ch);
+    VTTS_REQUIRE(b_rows_total % 64 == 0 && b_rows_total >= N + row_shift && b_rows_total <= 512 && row_shift >= 0,
+                 "vtts_dbg_umma_gemm: b_rows_total must be a multiple of 64 covering N + row_shift");
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {(uint64_t)K, 128};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {(uint32_t)ch, 64};
+        int rc = make_tmap_bf16(&ta, a_bf16, 2, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)b_rows_total};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {(uint32_t)ch, 64};
+        int rc = make_tmap_bf16(&tb, b_bf16, 2, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    const size_t smem = 1024 + (size_t)(128 + b_rows_total) * rowb + 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rowb == 128) {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        umma_probe_kernel<128><<<1, 128, smem, st>>>(ta, tb, d, N, K / ch, b_rows_total, row_shift, variant);
+    } else {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        umma_probe_kernel<64><<<1, 128, smem, st>>>(ta, tb, d, N, K / ch, b_rows_total, row_shift, variant);
+    }
+    VTTS_CHECK_LAUNCH();
+    return VTTS_OK;
+}
+
+// Single Conv1d layer through the tensor-core kernel, channels-first fp32 in/out (test hook).
+extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const float *res, float *y,
+                                  float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
+                                  float slope_in, float slope_out, vtts_stream_t stream) {
+    VTTS_REQUIRE(x && w && y, "vtts_dbg_conv1d_tc: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ci_pad = ci_pad_of(cin), n_pad = pad_to(cout, TM);
+    __nv_bfloat16 *a = nullptr, *wp = nullptr, *oa = nullptr;
+    float *ox = nullptr, *rcl = nullptr;
+    VTTS_CHECK_CUDA(cudaMalloc(&a, (size_t)B * L * ci_pad * 2));
+    VTTS_CHECK_CUDA(cudaMalloc(&wp, (size_t)ksize * n_pad * ci_pad * 2));
+    VTTS_CHECK_CUDA(cudaMalloc(&oa, (size_t)B * L * cout * 2));
+    VTTS_CHECK_CUDA(cudaMalloc(&ox, (size_t)B * L * cout * 4));
+    VTTS_CHECK_CUDA(cudaMalloc(&rcl, (size_t)B * L * cout * 4));
+    int rc = launch_cf_to_cl_bf16(x, a, B, cin, L, ci_pad, slope_in, st);
+    if (!rc) {
+        size_t n = (size_t)ksize * n_pad * ci_pad;
+        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad);
+    }
+    if (!rc && res) {
+        // channels-first -> channels-last fp32: reuse cl_to_cf with swapped roles (C <-> L)
+        rc = launch_cl_to_cf_f32(res, rcl, B, L, cout, st);  // treats input as (B, "L"=cout, "C"=L)
+    }
+    if (!rc) {
+        TcConvParams p{};
+        p.bias = bias; p.res = res ? rcl : nullptr; p.out_x = ox; p.out_a = y_act ? oa : nullptr; p.out_a_ld = cout;
+        p.slope_out = slope_out; p.n_total = cout; p.cout = cout; p.L_out = L; p.n_pos = L; p.out_stride = 1;
+        p.out_off0 = 0; p.taps = ksize; p.tap_off0 = -(ksize - 1) / 2 * dilation; p.tap_step = dilation;
+        TcLaunch Lc;
+        rc = tc_prepare(Lc, a, B, L, ci_pad, wp, n_pad, p);
+        if (!rc) rc = tc_launch(Lc, st);
+    }
+    if (!rc) rc = launch_cl_to_cf_f32(ox, y, B, cout, L, st);
+    if (!rc && y_act) rc = launch_cl_bf16_to_cf_f32(oa, y_act, B, cout, L, cout, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(a); cudaFree(wp); cudaFree(oa); cudaFree(ox); cudaFree(rcl);
+    if (!rc && e != cudaSuccess) return set_error(VTTS_E_CUDA, "vtts_dbg_conv1d_tc: %s", cudaGetErrorString(e));
+    return rc;
 }

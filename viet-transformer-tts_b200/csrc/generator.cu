@@ -24,8 +24,8 @@ int set_error(int code, const char *fmt, ...) {
 static int convT_out_len(int L, int s, int k, int p, int op) { return (L - 1) * s - 2 * p + k + op; }
 
 static void free_layer(Layer &l) {
-    cudaFree(l.w_fold); cudaFree(l.w_f32); cudaFree(l.bias); cudaFree(l.w_bf16);
-    l.w_fold = l.w_f32 = l.bias = nullptr; l.w_bf16 = nullptr;
+    cudaFree(l.w_fold); cudaFree(l.w_f32); cudaFree(l.bias); cudaFree(l.w_bf16); cudaFree(l.w_aux);
+    l.w_fold = l.w_f32 = l.bias = l.w_aux = nullptr; l.w_bf16 = nullptr;
 }
 
 }  // namespace vtts

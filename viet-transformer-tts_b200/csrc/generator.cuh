@@ -14,6 +14,7 @@ struct Layer {
     float *w_f32 = nullptr;  // fp32 packed [phase][ci][tap][co]
     float *bias = nullptr;   // fp32 (cout) or null
     __nv_bfloat16 *w_bf16 = nullptr;  // tcgen05 packing [tap][n][ci_pad] (conv_tc.cu)
+    float *w_aux = nullptr;  // output conv only: fp32 [oc][k][ci] for the channels-last kernel
     int ci_pad = 0;          // bf16 packing: padded input channels
     int n_total = 0;         // bf16 packing: rows per tap (cout, or s*cout for polyphase)
     bool has_bias = false;
