@@ -23,7 +23,9 @@
 
 #include <map>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 namespace vtts {
 namespace tc {
@@ -69,19 +71,25 @@ int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel
+// kernel (persistent: one CTA per SM loops over tiles; TMEM accumulator double-buffered so the
+// epilogue of tile t overlaps the MMAs of tile t+1)
 // ---------------------------------------------------------------------------------------------
-constexpr int TN = 256;          // time positions per CTA (UMMA N, TMEM columns)
-constexpr int TM = 128;          // output rows per CTA (UMMA M, TMEM lanes)
-constexpr int HALO_MAX = 64;     // (k-1)*d <= 64
+constexpr int TN = 256;            // time positions per tile (UMMA N, TMEM columns per accumulator)
+constexpr int TM = 128;            // output rows per tile (UMMA M, TMEM lanes)
+constexpr int HALO_MAX = 64;       // (k-1)*d <= 64
 constexpr int ACT_ROWS = TN + HALO_MAX;
-constexpr int BOX_ROWS = 64;     // activation TMA box height
-constexpr int PRODUCER_WARPS = 3;  // act producer, weight producer, MMA issuer
+constexpr int BOX_ROWS = 64;       // activation TMA box height
+constexpr int ACT_STAGES = 2;      // activation tiles in flight (one per K chunk)
+constexpr int W_STAGES = 8;        // weight tiles in flight (one per (chunk, tap))
+constexpr int ACC_STAGES = 2;      // TMEM accumulators
+constexpr int PRODUCER_WARPS = 3;  // activation producer, weight producer, MMA issuer
+constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
+constexpr int TC_THREADS = (PRODUCER_WARPS + EPI_WARPS) * 32;
 
 struct TcConvParams {
     // epilogue tensors (channels-last)
-    const float *bias;      // (n_total) or null  -- indexed by output row n
-    const float *bias_b;    // (B, n_total) or null
+    const float *bias;      // (cout) or null
+    const float *bias_b;    // (B, cout) or null -- per-batch global-conditioning bias (phases == 1 only)
     const float *res;       // (B, L_out, cout) fp32 or null
     float *out_x;           // (B, L_out, cout) fp32 or null
     __nv_bfloat16 *out_a;   // (B, L_out, out_a_ld) bf16 or null
@@ -95,16 +103,14 @@ struct TcConvParams {
     int L_out;
     int n_pos;              // time positions (GEMM N extent)
     int out_stride, out_off0;  // t_out = i * out_stride + out_off0 + phase
-    int chunks;             // K chunks (ci_pad / chunk_elems)
+    int chunks;             // K chunks (ci_pad / chunk channels)
     int taps, tap_off0, tap_step;
-    int act_stages, w_stages;
+    // tile schedule: tile -> (m block fastest, then time tile, then batch)
+    int m_blocks, t_tiles, total_tiles;
 };
 
-constexpr int EPI_WARPS = 8;
-constexpr int TC_THREADS = (PRODUCER_WARPS + EPI_WARPS) * 32;
-
 template <int ROWB>  // bytes per operand row: 128 (64 channels, SW128) or 64 (32 channels, SW64)
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const TcConvParams p) {
     constexpr int CH = ROWB / 2;                 // bf16 channels per chunk
@@ -118,30 +124,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         __trap();
     }
     uint8_t *s_act = smem;
-    uint8_t *s_w = smem + (size_t)p.act_stages * ACT_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + (size_t)p.w_stages * W_BYTES);
-    uint64_t *act_full = bars, *act_empty = bars + p.act_stages;
-    uint64_t *w_full = bars + 2 * p.act_stages, *w_empty = w_full + p.w_stages;
-    uint64_t *acc_full = w_empty + p.w_stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    uint8_t *s_w = smem + (size_t)ACT_STAGES * ACT_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + (size_t)W_STAGES * W_BYTES);
+    uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
+    uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
+    uint64_t *acc_full = w_empty + W_STAGES, *acc_empty = acc_full + ACC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = blockIdx.x * TN;       // first time position of this tile
-    const int n0 = blockIdx.y * TM;       // first output row
-    const int b = blockIdx.z;
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
     const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.act_stages; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
-        for (int s = 0; s < p.w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
+        for (int s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 2) {  // MMA warp owns the TMEM allocation
-        tmem_alloc(tmem_slot, TN);
+    if (warp == 2) {  // MMA warp owns the TMEM allocation (all 512 columns: 2 accumulators)
+        tmem_alloc(tmem_slot, ACC_STAGES * TN);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -153,122 +156,141 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
-            for (int c = 0; c < p.chunks; ++c) {
-                const int s = c % p.act_stages;
-                const uint32_t ph = (uint32_t)(c / p.act_stages) & 1u;
-                mbar_wait(&act_empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
-                for (int bx = 0; bx < nbox; ++bx)
-                    tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s],
-                                c * CH, i0 + min_off + bx * BOX_ROWS, b);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int rest = tile / p.m_blocks;
+                const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
+                for (int c = 0; c < p.chunks; ++c, ++it) {
+                    const uint32_t s = it % ACT_STAGES, ph = (it / ACT_STAGES) & 1u;
+                    mbar_wait(&act_empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
+                    for (int bx = 0; bx < nbox; ++bx)
+                        tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act,
+                                    &act_full[s], c * CH, i0 + min_off + bx * BOX_ROWS, b);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== weight producer: one 128-row tile per (chunk, tap) =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_w);
-            int it = 0;
-            for (int c = 0; c < p.chunks; ++c)
-                for (int j = 0; j < p.taps; ++j, ++it) {
-                    const int s = it % p.w_stages;
-                    const uint32_t ph = (uint32_t)(it / p.w_stages) & 1u;
-                    mbar_wait(&w_empty[s], ph ^ 1u);
-                    mbar_arrive_expect_tx(&w_full[s], (uint32_t)W_BYTES);
-                    tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
-                }
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.m_blocks) * TM;
+                for (int c = 0; c < p.chunks; ++c)
+                    for (int j = 0; j < p.taps; ++j, ++it) {
+                        const uint32_t s = it % W_STAGES, ph = (it / W_STAGES) & 1u;
+                        mbar_wait(&w_empty[s], ph ^ 1u);
+                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)W_BYTES);
+                        tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
+                    }
+            }
         }
     } else if (warp == 2) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(TM, TN);
-            int it = 0;
-            for (int c = 0; c < p.chunks; ++c) {
-                const int sa = c % p.act_stages;
-                mbar_wait(&act_full[sa], (uint32_t)(c / p.act_stages) & 1u);
-                const uint32_t act_base = smem_u32(s_act + (size_t)sa * ACT_BYTES);
-                for (int j = 0; j < p.taps; ++j, ++it) {
-                    const int sw = it % p.w_stages;
-                    mbar_wait(&w_full[sw], (uint32_t)(it / p.w_stages) & 1u);
-                    tc_fence_after();
-                    const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
-                    const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
+            uint32_t ia = 0, iw = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t buf = tl % ACC_STAGES;
+                mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * TN;
+                for (int c = 0; c < p.chunks; ++c, ++ia) {
+                    const uint32_t sa = ia % ACT_STAGES;
+                    mbar_wait(&act_full[sa], (ia / ACT_STAGES) & 1u);
+                    const uint32_t act_base = smem_u32(s_act + (size_t)sa * ACT_BYTES);
+                    for (int j = 0; j < p.taps; ++j, ++iw) {
+                        const uint32_t sw = iw % W_STAGES;
+                        mbar_wait(&w_full[sw], (iw / W_STAGES) & 1u);
+                        tc_fence_after();
+                        const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
+                        const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
 #pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks) {
-                        const uint64_t adesc = make_smem_desc(w_base + ks * 32, ROWB, 0);
-                        const uint64_t bdesc = make_smem_desc(act_base + row * ROWB + ks * 32, ROWB, 0);
-                        umma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)((c | j | ks) != 0));
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            const uint64_t adesc = make_smem_desc(w_base + ks * 32, ROWB, 0);
+                            const uint64_t bdesc = make_smem_desc(act_base + row * ROWB + ks * 32, ROWB, 0);
+                            umma_bf16(tmem_d, adesc, bdesc, idesc, (uint32_t)((c | j | ks) != 0));
+                        }
+                        umma_commit(&w_empty[sw]);   // weight stage reusable once these MMAs retire
                     }
-                    umma_commit(&w_empty[sw]);   // weight stage reusable once these MMAs retire
+                    umma_commit(&act_empty[sa]);     // activation stage reusable
                 }
-                umma_commit(&act_empty[sa]);     // activation stage reusable
+                umma_commit(&acc_full[buf]);         // accumulator complete -> epilogue
             }
-            umma_commit(acc_full);               // accumulator complete -> epilogue
         }
     } else {
         // ===== epilogue warps: thread = output row (channel), registers = time positions =====
         const int ew = warp - PRODUCER_WARPS;
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
-        const int rows_valid = p.n_total - n0;              // valid rows in this CTA
-        const int quarters_used = rows_valid >= TM ? 4 : (rows_valid + 31) / 32;
-        if (quarter < quarters_used) {
-            // the two warps sharing a quarter split the TN columns
-            constexpr int SHARERS = EPI_WARPS / 4;
-            constexpr int COLS_PER = TN / SHARERS;
-            const int col_lo = (ew / 4) * COLS_PER;
+        constexpr int SHARERS = EPI_WARPS / 4;              // warps sharing a quarter split the columns
+        constexpr int COLS_PER = TN / SHARERS;
+        const int col_lo = (ew / 4) * COLS_PER;
+        const long long sx = (long long)p.out_stride * p.cout;      // fp32 elements between time positions
+        const long long sa = (long long)p.out_stride * p.out_a_ld;  // bf16 elements between time positions
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            const int n0 = (tile % p.m_blocks) * TM;
+            const int rest = tile / p.m_blocks;
+            const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
+            const uint32_t buf = tl % ACC_STAGES;
             const int n = n0 + quarter * 32 + lane;         // global output row of this thread
             const bool row_ok = n < p.n_total;
             const int phase = row_ok ? n / p.cout : 0;
             const int co = row_ok ? n - phase * p.cout : 0;
             float bias = 0.f;
-            if (row_ok && p.bias) bias = __ldg(p.bias + n);
-            if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.n_total + n);
-            const size_t step = (size_t)p.out_stride * p.cout;       // elements between time positions
-            mbar_wait(acc_full, 0);
+            if (row_ok && p.bias) bias = __ldg(p.bias + co);
+            if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
+            const bool quarter_used = (n0 + quarter * 32) < p.n_total;   // warp-uniform
+            mbar_wait(&acc_full[buf], (tl / ACC_STAGES) & 1u);
             tc_fence_after();
-            for (int cg = 0; cg < COLS_PER; cg += 32) {
-                const int col = col_lo + cg;
-                if (i0 + col >= p.n_pos) break;             // warp-uniform: nothing valid beyond
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
-                tmem_ld_wait();
+            if (quarter_used) {
+                for (int cg = 0; cg < COLS_PER; cg += 32) {
+                    const int col = col_lo + cg;
+                    if (i0 + col >= p.n_pos) break;         // warp-uniform: nothing valid beyond
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN + (uint32_t)col, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int ibase = i0 + col + half * 16;
-                    const long long t_first = (long long)ibase * p.out_stride + p.out_off0 + phase;
-                    // offset of element e: off0 + e * step   (only dereferenced when valid)
-                    const long long off0 = ((long long)b * p.L_out + t_first) * p.cout + co;
-                    uint32_t okmask = 0;
-                    float rr[16], aa[16];
+                    for (int half = 0; half < 2; ++half) {
+                        const int ibase = i0 + col + half * 16;
+                        const long long t_first = (long long)ibase * p.out_stride + p.out_off0 + phase;
+                        const long long row0 = (long long)b * p.L_out + t_first;   // output row of element 0
+                        const long long xo = row0 * p.cout + co;
+                        const long long ao = row0 * p.out_a_ld + co;
+                        uint32_t okmask = 0;
+                        float rr[16], aa[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const long long t = t_first + (long long)e * p.out_stride;
-                        const bool ok = row_ok && (ibase + e) < p.n_pos && t >= 0 && t < p.L_out;
-                        okmask |= (ok ? 1u : 0u) << e;
-                        rr[e] = (ok && p.res) ? __ldg(p.res + off0 + (long long)e * (long long)step) : 0.f;
-                        aa[e] = (ok && p.accumulate) ? p.out_x[off0 + (long long)e * (long long)step] : 0.f;
-                    }
+                        for (int e = 0; e < 16; ++e) {
+                            const long long t = t_first + (long long)e * p.out_stride;
+                            const bool ok = row_ok && (ibase + e) < p.n_pos && t >= 0 && t < p.L_out;
+                            okmask |= (ok ? 1u : 0u) << e;
+                            rr[e] = (ok && p.res) ? __ldg(p.res + xo + e * sx) : 0.f;
+                            aa[e] = (ok && p.accumulate) ? p.out_x[xo + e * sx] : 0.f;
+                        }
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        if (okmask & (1u << e)) {
-                            const long long off = off0 + (long long)e * (long long)step;
-                            float val = __uint_as_float(v[half * 16 + e]) + bias;
-                            if (p.res) val = val + rr[e];
-                            if (p.accumulate) val = aa[e] + val;
-                            if (p.divide_by > 0.f) val = __fdiv_rn(val, p.divide_by);
-                            if (p.out_x) p.out_x[off] = val;
-                            if (p.out_a) {
-                                const long long rowi = (off - co) / p.cout;
-                                p.out_a[rowi * p.out_a_ld + co] = __float2bfloat16(lrelu(val, p.slope_out));
+                        for (int e = 0; e < 16; ++e) {
+                            if (okmask & (1u << e)) {
+                                float val = __uint_as_float(v[half * 16 + e]) + bias;
+                                if (p.res) val = val + rr[e];
+                                if (p.accumulate) val = aa[e] + val;
+                                if (p.divide_by > 0.f) val = __fdiv_rn(val, p.divide_by);
+                                if (p.out_x) p.out_x[xo + e * sx] = val;
+                                if (p.out_a) p.out_a[ao + e * sa] = __float2bfloat16(lrelu(val, p.slope_out));
                             }
                         }
                     }
                 }
             }
+            // all of this warp's tcgen05.ld have completed (wait::ld above): release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, TN);
+    if (warp == 2) tmem_dealloc(tmem_base, ACC_STAGES * TN);
 }
 
 struct TcLaunch {
@@ -276,13 +298,23 @@ struct TcLaunch {
     TcConvParams p;
     int rowb;
     dim3 grid;
-    int threads;
     size_t smem;
 };
 
-static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
-    return (size_t)act_stages * ACT_ROWS * rowb + (size_t)w_stages * TM * rowb +
-           (size_t)(2 * act_stages + 2 * w_stages + 1) * 8 + 16;
+static size_t tc_smem_bytes(int rowb) {
+    return (size_t)ACT_STAGES * ACT_ROWS * rowb + (size_t)W_STAGES * TM * rowb +
+           (size_t)(2 * ACT_STAGES + 2 * W_STAGES + 2 * ACC_STAGES) * 8 + 16;
+}
+
+static int tc_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
 }
 
 static int tc_launch(const TcLaunch &L, cudaStream_t st) {
@@ -292,14 +324,14 @@ static int tc_launch(const TcLaunch &L, cudaStream_t st) {
             VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr128 = true;
         }
-        conv_tc_kernel<128><<<L.grid, L.threads, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
+        conv_tc_kernel<128><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
     } else {
         static bool attr64 = false;
         if (!attr64) {
             VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr64 = true;
         }
-        conv_tc_kernel<64><<<L.grid, L.threads, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
+        conv_tc_kernel<64><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
     }
     VTTS_CHECK_LAUNCH();
     return VTTS_OK;
@@ -314,16 +346,18 @@ static int tc_prepare(TcLaunch &L, const __nv_bfloat16 *act, int B, int L_in, in
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int span = last_off > p.tap_off0 ? last_off - p.tap_off0 : p.tap_off0 - last_off;
     if (span > HALO_MAX) return set_error(VTTS_E_UNSUPPORTED, "tc: tap span %d > %d", span, HALO_MAX);
+    if (p.bias_b && p.n_total != p.cout) return set_error(VTTS_E_INVALID, "tc: per-batch bias needs a single phase");
     L.rowb = rowb;
     p.chunks = ci_pad / ch;
-    // pipeline depth: single-chunk layers keep one activation stage and deeper weight stages
-    if (p.chunks == 1) { p.act_stages = 1; p.w_stages = 4; }
-    else { p.act_stages = 2; p.w_stages = 2; }
-    if (p.w_stages > p.chunks * p.taps) p.w_stages = p.chunks * p.taps;
+    p.m_blocks = n_pad / TM;
+    p.t_tiles = ceil_div(p.n_pos, TN);
+    const long long total = (long long)p.m_blocks * p.t_tiles * B;
+    if (total > 0x7fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "tc: too many tiles");
+    p.total_tiles = (int)total;
     L.p = p;
-    L.threads = TC_THREADS;
-    L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
-    L.grid = dim3((unsigned)ceil_div(p.n_pos, TN), (unsigned)(n_pad / TM), (unsigned)B);
+    L.smem = tc_smem_bytes(rowb);
+    const int sms = tc_num_sms();
+    L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     {
         uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)L_in, (uint64_t)B};
         uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)L_in};
@@ -523,6 +557,30 @@ int tc_workspace_bytes(const VttsGen *h, int B, int T, size_t *bytes) {
 }
 
 namespace {
+// VTTS_PROFILE=1: per-launch CUDA-event timing of the tcgen05 path, printed to stderr after the forward
+struct ProfRec { cudaEvent_t a, b; int kind, cin, cout, k, d, B, L; };
+static std::vector<ProfRec> g_prof;
+static bool prof_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VTTS_PROFILE"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+static void prof_report() {
+    if (g_prof.empty()) return;
+    cudaDeviceSynchronize();
+    double total = 0, tflop = 0;
+    for (auto &r : g_prof) {
+        float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+        const double fl = 2.0 * r.cin * r.cout * r.k * (double)r.B * r.L;   // conv: per output step; convT: per input step
+        fprintf(stderr, "[vtts-prof] kind=%d cin=%4d cout=%4d k=%2d d=%d L=%7d  %8.3f ms  %7.1f TFLOP/s\n", r.kind, r.cin,
+                r.cout, r.k, r.d, r.L, ms, fl / (ms * 1e-3) / 1e12);
+        total += ms; tflop += fl;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    fprintf(stderr, "[vtts-prof] total %.3f ms over %zu conv launches, %.1f TFLOP/s\n", total, g_prof.size(),
+            tflop / (total * 1e-3) / 1e12);
+    g_prof.clear();
+}
 // one conv layer on the tensor cores
 static int run_conv(VttsGen *h, const Layer &l, const __nv_bfloat16 *act, int B, int L_in, int L_out, TcConvParams p,
                     cudaStream_t st) {
@@ -542,7 +600,15 @@ static int run_conv(VttsGen *h, const Layer &l, const __nv_bfloat16 *act, int B,
     TcLaunch L;
     int rc = tc_prepare(L, act, B, L_in, l.ci_pad, l.w_bf16, pad_to(l.n_total, TM), p);
     if (rc) return rc;
+    ProfRec pr{};
+    if (prof_enabled()) {
+        cudaEventCreate(&pr.a); cudaEventCreate(&pr.b);
+        pr.kind = l.info.kind; pr.cin = l.info.cin; pr.cout = l.info.cout; pr.k = l.info.ksize; pr.d = l.info.dilation;
+        pr.B = B; pr.L = transposed ? L_in : L_out;
+        cudaEventRecord(pr.a, st);
+    }
     if ((rc = tc_launch(L, st))) return rc;
+    if (prof_enabled()) { cudaEventRecord(pr.b, st); g_prof.push_back(pr); }
     h->launch_count++;
     return VTTS_OK;
 }
@@ -665,6 +731,7 @@ int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, in
             h->launch_count++;
         }
     }
+    if (prof_enabled()) prof_report();
     return VTTS_OK;
 }
 
