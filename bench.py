@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--ref-utts", type=int, default=2, help="utterances per step for the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -311,7 +311,7 @@ def main():
             "metric": "synthesized audio sec/sec (inverse RTF)", "value": value, "unit": "audio_s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
             "config": {
                 "workload": "configs[1]: LengthRegulator (16,120,256) + HiFi-GAN V1, 22.05 kHz, batch 16/GPU",
                 "precision": precision, "batch_per_gpu": args.batch, "padded_mel_frames": padded_frames,

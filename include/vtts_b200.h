@@ -126,7 +126,8 @@ int vtts_gen_load_layer(VttsGen *h, int layer, const float *weight_v, const floa
                         const float *bias, vtts_stream_t stream);
 
 #define VTTS_PRECISION_FP32 0 /* CUDA-core fp32 direct convolution (in-repo reference path) */
-#define VTTS_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate/residual, fp32 output conv */
+#define VTTS_PRECISION_BF16 1 /* tcgen05, bf16 operands, fp32 accumulate/residual, fp32 output conv */
+#define VTTS_PRECISION_FP16 2 /* same kernels and rate with fp16 operands (8x smaller rounding error) */
 
 int vtts_gen_workspace_bytes(const VttsGen *h, int B, int T, int precision, size_t *bytes);
 
@@ -157,11 +158,11 @@ int vtts_dbg_conv1d_fp32(const float *x, const float *w, const float *bias, cons
 int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float *d, int M, int N, int K,
                        int a_rows_total, int row_shift, int variant, vtts_stream_t stream);
 
-/* One Conv1d layer through the tcgen05 kernel (bf16 operands, fp32 accumulate), channels-first
+/* One Conv1d layer through the tcgen05 kernel (bf16 or fp16 operands, fp32 accumulate), channels-first
  * fp32 in/out: y = conv(bf16(lrelu_in(x))) + bias [+ res]; y_act (optional) = bf16(lrelu_out(y)). */
 int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const float *res, float *y,
                        float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
-                       float slope_in, float slope_out, vtts_stream_t stream);
+                       float slope_in, float slope_out, int fp16, vtts_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -80,10 +81,20 @@ int launch_pack_convT_fp32(const float *w, float *packed, int cin, int cout, int
 
 // layout helpers (pack.cu)
 // (B, C, L) fp32 channels-first <-> (B, L, C) channels-last
-int launch_cf_to_cl_bf16(const float *x, __nv_bfloat16 *y, int B, int C, int L, int Cpad,
-                         float slope, cudaStream_t stream);
+// 16-bit operand formats of the tensor-core path
+enum { VTTS_FMT_BF16 = 0, VTTS_FMT_FP16 = 1 };
+__device__ __forceinline__ uint16_t cvt16(float v, int fmt) {
+    if (fmt == VTTS_FMT_BF16) return __bfloat16_as_ushort(__float2bfloat16(v));
+    v = fminf(fmaxf(v, -65504.f), 65504.f);  // saturate instead of overflowing to inf
+    return __half_as_ushort(__float2half_rn(v));
+}
+__device__ __forceinline__ float cvt16_to_f32(uint16_t u, int fmt) {
+    return fmt == VTTS_FMT_BF16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
+}
+int launch_cf_to_cl_16(const float *x, uint16_t *y, int B, int C, int L, int Cpad, float slope, int fmt,
+                       cudaStream_t stream);
 int launch_cl_to_cf_f32(const float *x, float *y, int B, int C, int L, cudaStream_t stream);
-int launch_cl_bf16_to_cf_f32(const __nv_bfloat16 *x, float *y, int B, int C, int L, int Cld,
-                             cudaStream_t stream);
+int launch_cl_16_to_cf_f32(const uint16_t *x, float *y, int B, int C, int L, int Cld, int fmt,
+                           cudaStream_t stream);
 
 }  // namespace vtts

@@ -59,7 +59,7 @@ int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t 
                           : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr,
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr,
                      bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -92,11 +92,12 @@ struct TcConvParams {
     const float *bias_b;    // (B, cout) or null -- per-batch global-conditioning bias (phases == 1 only)
     const float *res;       // (B, L_out, cout) fp32 or null
     float *out_x;           // (B, L_out, cout) fp32 or null
-    __nv_bfloat16 *out_a;   // (B, L_out, out_a_ld) bf16 or null
+    uint16_t *out_a;        // (B, L_out, out_a_ld) bf16/fp16 or null
     int out_a_ld;
     float slope_out;        // LeakyReLU slope applied to the bf16 copy (1 = identity)
     int accumulate;         // out_x = out_x_old + value
-    float divide_by;        // > 0: value /= divide_by
+    float divide_by;        // > 0: value /= divide_by (applied as * inv_div on this path)
+    float inv_div;
     // geometry
     int n_total;            // valid output rows (cout * phases)
     int cout;               // channels per phase
@@ -109,7 +110,111 @@ struct TcConvParams {
     int m_blocks, t_tiles, total_tiles;
 };
 
-template <int ROWB>  // bytes per operand row: 128 (64 channels, SW128) or 64 (32 channels, SW64)
+// ---- epilogue helpers -------------------------------------------------------------------------------
+// max(v, v*slope) == LeakyReLU for 0 <= slope <= 1 (checked on the host); slope 1 = identity
+__device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
+
+// Fast path for one 32-column group that is entirely valid.  COUT_CT > 0: compile-time row pitch
+// (out_stride == 1, out_a_ld == cout) so every access is base + immediate.
+// MODE 0: operand copy only; MODE 1: residual + fp32 stream + operand copy; MODE 2: runtime flags.
+template <int FMT, int COUT_CT, int MODE>
+__device__ __forceinline__ void epi_group_fast(const uint32_t (&v)[32], float bias, const TcConvParams &p,
+                                               long long xo, long long ao, long long sx_rt, long long sa_rt) {
+    const long long sx = COUT_CT ? (long long)COUT_CT : sx_rt;
+    const long long sa = COUT_CT ? (long long)COUT_CT : sa_rt;
+    if (MODE == 0) {
+        uint16_t *pa = p.out_a + ao;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pa[e * sa] = cvt16(lrelu_max(__uint_as_float(v[e]) + bias, p.slope_out), FMT);
+    } else if (MODE == 1) {
+        const float *pr = p.res + xo;
+        float *px = p.out_x + xo;
+        uint16_t *pa = p.out_a + ao;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float rr[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) rr[e] = __ldg(pr + (h * 16 + e) * sx);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float val = (__uint_as_float(v[h * 16 + e]) + bias) + rr[e];
+                px[(h * 16 + e) * sx] = val;
+                pa[(h * 16 + e) * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float rr[16], aa[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                rr[e] = p.res ? __ldg(p.res + xo + (h * 16 + e) * sx) : 0.f;
+                aa[e] = p.accumulate ? p.out_x[xo + (h * 16 + e) * sx] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float val = __uint_as_float(v[h * 16 + e]) + bias;
+                if (p.res) val = val + rr[e];
+                if (p.accumulate) val = aa[e] + val;
+                if (p.divide_by > 0.f) val = val * p.inv_div;
+                if (p.out_x) p.out_x[xo + (h * 16 + e) * sx] = val;
+                if (p.out_a) p.out_a[ao + (h * 16 + e) * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
+            }
+        }
+    }
+}
+
+// Generic path: per-element validity (tile edges, polyphase output bounds, padded rows).
+template <int FMT>
+__device__ __forceinline__ void epi_group_edge(const uint32_t (&v)[32], float bias, const TcConvParams &p, bool row_ok,
+                                               int ibase0, long long t_first0, long long xo0, long long ao0,
+                                               long long sx, long long sa) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t okmask = 0;
+        float rr[16], aa[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int ee = h * 16 + e;
+            const long long t = t_first0 + (long long)ee * p.out_stride;
+            const bool ok = row_ok && (ibase0 + ee) < p.n_pos && t >= 0 && t < p.L_out;
+            okmask |= (ok ? 1u : 0u) << e;
+            rr[e] = (ok && p.res) ? __ldg(p.res + xo0 + ee * sx) : 0.f;
+            aa[e] = (ok && p.accumulate) ? p.out_x[xo0 + ee * sx] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            if (okmask & (1u << e)) {
+                const int ee = h * 16 + e;
+                float val = __uint_as_float(v[ee]) + bias;
+                if (p.res) val = val + rr[e];
+                if (p.accumulate) val = aa[e] + val;
+                if (p.divide_by > 0.f) val = val * p.inv_div;
+                if (p.out_x) p.out_x[xo0 + ee * sx] = val;
+                if (p.out_a) p.out_a[ao0 + ee * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
+            }
+        }
+    }
+}
+
+template <int FMT, int MODE>
+__device__ __forceinline__ void epi_group_dispatch(int cout_ct, const uint32_t (&v)[32], float bias,
+                                                   const TcConvParams &p, long long xo, long long ao, long long sx,
+                                                   long long sa) {
+    if (MODE != 2) {
+        switch (cout_ct) {
+            case 32: epi_group_fast<FMT, 32, MODE>(v, bias, p, xo, ao, sx, sa); return;
+            case 64: epi_group_fast<FMT, 64, MODE>(v, bias, p, xo, ao, sx, sa); return;
+            case 128: epi_group_fast<FMT, 128, MODE>(v, bias, p, xo, ao, sx, sa); return;
+            case 256: epi_group_fast<FMT, 256, MODE>(v, bias, p, xo, ao, sx, sa); return;
+            default: break;
+        }
+    }
+    epi_group_fast<FMT, 0, MODE>(v, bias, p, xo, ao, sx, sa);
+}
+
+// ROWB: bytes per operand row: 128 (64 channels, SW128) or 64 (32 channels, SW64); FMT: 0 bf16, 1 fp16
+template <int ROWB, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const TcConvParams p) {
@@ -189,7 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     } else if (warp == 2) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(TM, TN);
+            constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
             uint32_t ia = 0, iw = 0, tl = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
@@ -227,58 +332,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         constexpr int COLS_PER = TN / SHARERS;
         const int col_lo = (ew / 4) * COLS_PER;
         const long long sx = (long long)p.out_stride * p.cout;      // fp32 elements between time positions
-        const long long sa = (long long)p.out_stride * p.out_a_ld;  // bf16 elements between time positions
+        const long long sa = (long long)p.out_stride * p.out_a_ld;  // 16-bit elements between time positions
+        // kernel-uniform epilogue specialisation
+        const bool plain = !p.accumulate && p.divide_by <= 0.f;
+        const int mode = (plain && !p.res && !p.out_x && p.out_a) ? 0 : (plain && p.res && p.out_x && p.out_a) ? 1 : 2;
+        const int cout_ct = (p.out_stride == 1 && p.out_a_ld == p.cout) ? p.cout : 0;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
             const int n0 = (tile % p.m_blocks) * TM;
             const int rest = tile / p.m_blocks;
             const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
             const uint32_t buf = tl % ACC_STAGES;
-            const int n = n0 + quarter * 32 + lane;         // global output row of this thread
+            const int nq = n0 + quarter * 32;               // first output row of this warp
+            const int n = nq + lane;                        // global output row of this thread
             const bool row_ok = n < p.n_total;
-            const int phase = row_ok ? n / p.cout : 0;
-            const int co = row_ok ? n - phase * p.cout : 0;
+            const int phase = nq / p.cout;                  // warp-uniform (cout is a multiple of 32)
+            const int co = n - phase * p.cout;
             float bias = 0.f;
             if (row_ok && p.bias) bias = __ldg(p.bias + co);
             if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
-            const bool quarter_used = (n0 + quarter * 32) < p.n_total;   // warp-uniform
+            const bool quarter_used = nq < p.n_total;       // warp-uniform
+            const bool rows_full = nq + 32 <= p.n_total;    // warp-uniform
             mbar_wait(&acc_full[buf], (tl / ACC_STAGES) & 1u);
             tc_fence_after();
             if (quarter_used) {
                 for (int cg = 0; cg < COLS_PER; cg += 32) {
                     const int col = col_lo + cg;
-                    if (i0 + col >= p.n_pos) break;         // warp-uniform: nothing valid beyond
+                    const int ibase = i0 + col;
+                    if (ibase >= p.n_pos) break;            // warp-uniform: nothing valid beyond
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN + (uint32_t)col, v);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int ibase = i0 + col + half * 16;
-                        const long long t_first = (long long)ibase * p.out_stride + p.out_off0 + phase;
-                        const long long row0 = (long long)b * p.L_out + t_first;   // output row of element 0
-                        const long long xo = row0 * p.cout + co;
-                        const long long ao = row0 * p.out_a_ld + co;
-                        uint32_t okmask = 0;
-                        float rr[16], aa[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const long long t = t_first + (long long)e * p.out_stride;
-                            const bool ok = row_ok && (ibase + e) < p.n_pos && t >= 0 && t < p.L_out;
-                            okmask |= (ok ? 1u : 0u) << e;
-                            rr[e] = (ok && p.res) ? __ldg(p.res + xo + e * sx) : 0.f;
-                            aa[e] = (ok && p.accumulate) ? p.out_x[xo + e * sx] : 0.f;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            if (okmask & (1u << e)) {
-                                float val = __uint_as_float(v[half * 16 + e]) + bias;
-                                if (p.res) val = val + rr[e];
-                                if (p.accumulate) val = aa[e] + val;
-                                if (p.divide_by > 0.f) val = __fdiv_rn(val, p.divide_by);
-                                if (p.out_x) p.out_x[xo + e * sx] = val;
-                                if (p.out_a) p.out_a[ao + e * sa] = __float2bfloat16(lrelu(val, p.slope_out));
-                            }
-                        }
+                    const long long t_first = (long long)ibase * p.out_stride + p.out_off0 + phase;
+                    const long long t_last = t_first + 31LL * p.out_stride;
+                    const long long row0 = (long long)b * p.L_out + t_first;   // output row of element 0
+                    const long long xo = row0 * p.cout + co;
+                    const long long ao = row0 * p.out_a_ld + co;
+                    const bool full = rows_full && (ibase + 32 <= p.n_pos) && t_first >= 0 && t_last < p.L_out;
+                    if (full) {
+                        if (mode == 0) epi_group_dispatch<FMT, 0>(cout_ct, v, bias, p, xo, ao, sx, sa);
+                        else if (mode == 1) epi_group_dispatch<FMT, 1>(cout_ct, v, bias, p, xo, ao, sx, sa);
+                        else epi_group_dispatch<FMT, 2>(cout_ct, v, bias, p, xo, ao, sx, sa);
+                    } else {
+                        epi_group_edge<FMT>(v, bias, p, row_ok, ibase, t_first, xo, ao, sx, sa);
                     }
                 }
             }
@@ -296,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
 struct TcLaunch {
     CUtensorMap tm_act, tm_w;
     TcConvParams p;
-    int rowb;
+    int rowb, fmt;
     dim3 grid;
     size_t smem;
 };
@@ -317,29 +413,26 @@ static int tc_num_sms() {
     return sms;
 }
 
-static int tc_launch(const TcLaunch &L, cudaStream_t st) {
-    if (L.rowb == 128) {
-        static bool attr128 = false;
-        if (!attr128) {
-            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr128 = true;
-        }
-        conv_tc_kernel<128><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
-    } else {
-        static bool attr64 = false;
-        if (!attr64) {
-            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr64 = true;
-        }
-        conv_tc_kernel<64><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
+template <int ROWB, int FMT>
+static int tc_launch_t(const TcLaunch &L, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
     }
+    conv_tc_kernel<ROWB, FMT><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
     VTTS_CHECK_LAUNCH();
     return VTTS_OK;
 }
 
+static int tc_launch(const TcLaunch &L, cudaStream_t st) {
+    if (L.rowb == 128) return L.fmt == VTTS_FMT_BF16 ? tc_launch_t<128, 0>(L, st) : tc_launch_t<128, 1>(L, st);
+    return L.fmt == VTTS_FMT_BF16 ? tc_launch_t<64, 0>(L, st) : tc_launch_t<64, 1>(L, st);
+}
+
 // Build a launch for one layer.  act: (B, L_in, ci_pad) bf16; w: [taps][n_pad][ci_pad] bf16.
-static int tc_prepare(TcLaunch &L, const __nv_bfloat16 *act, int B, int L_in, int ci_pad,
-                      const __nv_bfloat16 *w, int n_pad, TcConvParams p) {
+static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in, int ci_pad,
+                      const uint16_t *w, int n_pad, TcConvParams p) {
     const int rowb = (ci_pad % 64 == 0) ? 128 : 64;
     const int ch = rowb / 2;
     if (ci_pad % ch != 0) return set_error(VTTS_E_UNSUPPORTED, "tc: ci_pad %d not a multiple of %d", ci_pad, ch);
@@ -347,7 +440,11 @@ static int tc_prepare(TcLaunch &L, const __nv_bfloat16 *act, int B, int L_in, in
     const int span = last_off > p.tap_off0 ? last_off - p.tap_off0 : p.tap_off0 - last_off;
     if (span > HALO_MAX) return set_error(VTTS_E_UNSUPPORTED, "tc: tap span %d > %d", span, HALO_MAX);
     if (p.bias_b && p.n_total != p.cout) return set_error(VTTS_E_INVALID, "tc: per-batch bias needs a single phase");
+    if (p.slope_out < 0.f || p.slope_out > 1.f) return set_error(VTTS_E_UNSUPPORTED, "tc: LeakyReLU slope %g outside [0,1]", p.slope_out);
+    if (p.out_a && p.cout % 32 != 0) return set_error(VTTS_E_UNSUPPORTED, "tc: cout %d not a multiple of 32", p.cout);
     L.rowb = rowb;
+    L.fmt = fmt;
+    p.inv_div = p.divide_by > 0.f ? 1.f / p.divide_by : 1.f;
     p.chunks = ci_pad / ch;
     p.m_blocks = n_pad / TM;
     p.t_tiles = ceil_div(p.n_pos, TN);
@@ -380,7 +477,7 @@ static int tc_prepare(TcLaunch &L, const __nv_bfloat16 *act, int B, int L_in, in
 // ---------------------------------------------------------------------------------------------
 // Conv1d (cout,cin,k): n = co, tap j = kernel index.
 // ConvTranspose1d (cin,cout,k), stride s: n = q*cout + co, tap j reads x[i0 - j], weight index q + j*s.
-__global__ void pack_tc_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int kind, int cin,
+__global__ void pack_tc_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int fmt, int kind, int cin,
                                int cout, int k, int s, int taps, int n_pad, int ci_pad) {
     const size_t total = (size_t)taps * n_pad * ci_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -396,7 +493,7 @@ __global__ void pack_tc_kernel(const float *__restrict__ w, __nv_bfloat16 *__res
                 if (q < s) v = w[((size_t)ci * cout + co) * k + q + j * s];
             }
         }
-        out[idx] = __float2bfloat16(v);
+        out[idx] = cvt16(v, fmt);
     }
 }
 
@@ -459,11 +556,13 @@ int tc_pack_layer(VttsGen *h, int layer, cudaStream_t st) {
     l.n_total = transposed ? s * cout : cout;
     const int n_pad = pad_to(l.n_total, TM);
     const size_t n = (size_t)taps * n_pad * l.ci_pad;
-    if (!l.w_bf16) VTTS_CHECK_CUDA(cudaMalloc(&l.w_bf16, n * sizeof(__nv_bfloat16)));
     int blocks = (int)((n + 255) / 256);
     if (blocks > 8192) blocks = 8192;
-    pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w_bf16, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad);
-    VTTS_CHECK_LAUNCH();
+    for (int fmt = 0; fmt < 2; ++fmt) {
+        if (!l.w16[fmt]) VTTS_CHECK_CUDA(cudaMalloc(&l.w16[fmt], n * sizeof(uint16_t)));
+        pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w16[fmt], fmt, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad);
+        VTTS_CHECK_LAUNCH();
+    }
     if (layer == h->idx_post) {
         if (!l.w_aux) VTTS_CHECK_CUDA(cudaMalloc(&l.w_aux, (size_t)cin * cout * k * sizeof(float)));
         pack_post_kernel<<<ceil_div(cin * cout * k, 256), 256, 0, st>>>(l.w_fold, l.w_aux, cout, cin, k);
@@ -517,8 +616,8 @@ static TcPlan tc_plan(const VttsGen *h, int T) {
     return p;
 }
 struct TcBuffers {
-    __nv_bfloat16 *a_in;   // input operand (B, T, ci_pad)
-    __nv_bfloat16 *a_u, *a_p, *a_q, *a_t, *a_c;  // bf16 operand copies (max stage size)
+    uint16_t *a_in;   // input operand (B, T, ci_pad)
+    uint16_t *a_u, *a_p, *a_q, *a_t, *a_c;  // 16-bit operand copies (max stage size)
     float *x_u, *x_p, *x_q, *x_cs;                // fp32 residual stream
     float *gb;                                    // (B, channels) global conditioning bias
     float *tmp;                                   // fp32 staging for dumps / conditioning input
@@ -532,12 +631,12 @@ static TcBuffers tc_carve(const VttsGen *h, int B, int T, void *ws) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes, 1024); return r; };
     TcBuffers b{};
-    b.a_in = (__nv_bfloat16 *)take(in_pad * 2);
-    b.a_u = (__nv_bfloat16 *)take(elems * 2);
-    b.a_p = (__nv_bfloat16 *)take(elems * 2);
-    b.a_q = (__nv_bfloat16 *)take(elems * 2);
-    b.a_t = (__nv_bfloat16 *)take(elems * 2);
-    b.a_c = (__nv_bfloat16 *)take(elems * 2);
+    b.a_in = (uint16_t *)take(in_pad * 2);
+    b.a_u = (uint16_t *)take(elems * 2);
+    b.a_p = (uint16_t *)take(elems * 2);
+    b.a_q = (uint16_t *)take(elems * 2);
+    b.a_t = (uint16_t *)take(elems * 2);
+    b.a_c = (uint16_t *)take(elems * 2);
     b.x_u = (float *)take(elems * 4);
     b.x_p = (float *)take(elems * 4);
     b.x_q = (float *)take(elems * 4);
@@ -582,7 +681,7 @@ static void prof_report() {
     g_prof.clear();
 }
 // one conv layer on the tensor cores
-static int run_conv(VttsGen *h, const Layer &l, const __nv_bfloat16 *act, int B, int L_in, int L_out, TcConvParams p,
+static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, int B, int L_in, int L_out, TcConvParams p,
                     cudaStream_t st) {
     const bool transposed = l.info.kind == 1;
     const int s = transposed ? l.stride : 1;
@@ -598,7 +697,7 @@ static int run_conv(VttsGen *h, const Layer &l, const __nv_bfloat16 *act, int B,
         p.out_stride = 1; p.out_off0 = 0; p.n_pos = L_in;
     }
     TcLaunch L;
-    int rc = tc_prepare(L, act, B, L_in, l.ci_pad, l.w_bf16, pad_to(l.n_total, TM), p);
+    int rc = tc_prepare(L, fmt, act, B, L_in, l.ci_pad, l.w16[fmt], pad_to(l.n_total, TM), p);
     if (rc) return rc;
     ProfRec pr{};
     if (prof_enabled()) {
@@ -614,7 +713,7 @@ static int run_conv(VttsGen *h, const Layer &l, const __nv_bfloat16 *act, int B,
 }
 }  // namespace
 
-int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, int T, void *workspace,
+int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, int B, int T, void *workspace,
                size_t workspace_bytes, int dump_stage, float *dump_out, cudaStream_t st) {
     const VttsGenConfig &cfg = h->cfg;
     char why[128];
@@ -644,17 +743,17 @@ int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, in
     }
     // input layout change: (B, Cin, T) fp32 -> (B, T, ci_pad) bf16
     const Layer &pre = h->layers[h->idx_pre];
-    if ((rc = launch_cf_to_cl_bf16(c, bf.a_in, B, cfg.in_channels, T, pre.ci_pad, 1.f, st))) return rc;
+    if ((rc = launch_cf_to_cl_16(c, bf.a_in, B, cfg.in_channels, T, pre.ci_pad, 1.f, fmt, st))) return rc;
     h->launch_count++;
     {   // input_conv -> bf16 LeakyReLU'd operand for upsample 0 (fp32 copy only when dumped)
         TcConvParams p{};
         p.bias_b = bias_b;
         p.out_a = bf.a_c; p.out_a_ld = cfg.channels; p.slope_out = cfg.lrelu_slope;
         p.out_x = (dump_stage == 0) ? bf.x_cs : nullptr;
-        if ((rc = run_conv(h, pre, bf.a_in, B, T, T, p, st))) return rc;
+        if ((rc = run_conv(h, fmt, pre, bf.a_in, B, T, T, p, st))) return rc;
         if ((rc = dump_f32(0, bf.x_cs, cfg.channels, T))) return rc;
     }
-    const __nv_bfloat16 *cur_a = bf.a_c;
+    const uint16_t *cur_a = bf.a_c;
     int L = T;
     for (int i = 0; i < cfg.num_upsamples; ++i) {
         const Layer &u = h->layers[h->idx_up[i]];
@@ -663,25 +762,25 @@ int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, in
         {   // upsample: fp32 residual stream x_u + bf16 operand a_u = lrelu(x_u)
             TcConvParams p{};
             p.out_x = bf.x_u; p.out_a = bf.a_u; p.out_a_ld = C; p.slope_out = cfg.lrelu_slope;
-            if ((rc = run_conv(h, u, cur_a, B, L, Lo, p, st))) return rc;
+            if ((rc = run_conv(h, fmt, u, cur_a, B, L, Lo, p, st))) return rc;
             if ((rc = dump_f32(2 * i + 1, bf.x_u, C, Lo))) return rc;
         }
         const bool last_stage = (i == cfg.num_upsamples - 1);
         for (int j = 0; j < cfg.num_blocks; ++j) {
             const float *yx = bf.x_u;
-            const __nv_bfloat16 *ya = bf.a_u;
+            const uint16_t *ya = bf.a_u;
             const int nu = cfg.num_dilations[j];
             for (int m = 0; m < nu; ++m) {
                 const bool last = (m == nu - 1);
                 float *nx = last ? bf.x_cs : ((m & 1) ? bf.x_q : bf.x_p);
-                __nv_bfloat16 *na = (m & 1) ? bf.a_q : bf.a_p;
+                uint16_t *na = (m & 1) ? bf.a_q : bf.a_p;
                 const Layer &l1 = h->layers[h->idx_c1[i][j][m]];
                 const Layer *fin = &l1;
-                const __nv_bfloat16 *fin_in = ya;
+                const uint16_t *fin_in = ya;
                 if (cfg.use_additional_convs) {
                     TcConvParams p1{};  // xt = conv1(lrelu(x)); only its LeakyReLU'd bf16 copy is needed
                     p1.out_a = bf.a_t; p1.out_a_ld = C; p1.slope_out = cfg.lrelu_slope;
-                    if ((rc = run_conv(h, l1, ya, B, Lo, Lo, p1, st))) return rc;
+                    if ((rc = run_conv(h, fmt, l1, ya, B, Lo, Lo, p1, st))) return rc;
                     fin = &h->layers[h->idx_c2[i][j][m]];
                     fin_in = bf.a_t;
                 }
@@ -699,7 +798,7 @@ int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, in
                 } else {
                     p2.out_a = na; p2.out_a_ld = C; p2.slope_out = cfg.lrelu_slope;
                 }
-                if ((rc = run_conv(h, *fin, fin_in, B, Lo, Lo, p2, st))) return rc;
+                if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st))) return rc;
                 yx = nx; ya = na;
             }
         }
@@ -846,21 +945,22 @@ extern "C" int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float 
 // Single Conv1d layer through the tensor-core kernel, channels-first fp32 in/out (test hook).
 extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const float *res, float *y,
                                   float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
-                                  float slope_in, float slope_out, vtts_stream_t stream) {
+                                  float slope_in, float slope_out, int fp16, vtts_stream_t stream) {
     VTTS_REQUIRE(x && w && y, "vtts_dbg_conv1d_tc: null pointer");
+    const int fmt = fp16 ? VTTS_FMT_FP16 : VTTS_FMT_BF16;
     cudaStream_t st = (cudaStream_t)stream;
     const int ci_pad = ci_pad_of(cin), n_pad = pad_to(cout, TM);
-    __nv_bfloat16 *a = nullptr, *wp = nullptr, *oa = nullptr;
+    uint16_t *a = nullptr, *wp = nullptr, *oa = nullptr;
     float *ox = nullptr, *rcl = nullptr;
     VTTS_CHECK_CUDA(cudaMalloc(&a, (size_t)B * L * ci_pad * 2));
     VTTS_CHECK_CUDA(cudaMalloc(&wp, (size_t)ksize * n_pad * ci_pad * 2));
     VTTS_CHECK_CUDA(cudaMalloc(&oa, (size_t)B * L * cout * 2));
     VTTS_CHECK_CUDA(cudaMalloc(&ox, (size_t)B * L * cout * 4));
     VTTS_CHECK_CUDA(cudaMalloc(&rcl, (size_t)B * L * cout * 4));
-    int rc = launch_cf_to_cl_bf16(x, a, B, cin, L, ci_pad, slope_in, st);
+    int rc = launch_cf_to_cl_16(x, a, B, cin, L, ci_pad, slope_in, fmt, st);
     if (!rc) {
         size_t n = (size_t)ksize * n_pad * ci_pad;
-        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad);
+        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, fmt, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad);
     }
     if (!rc && res) {
         // channels-first -> channels-last fp32: reuse cl_to_cf with swapped roles (C <-> L)
@@ -872,11 +972,11 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
         p.slope_out = slope_out; p.n_total = cout; p.cout = cout; p.L_out = L; p.n_pos = L; p.out_stride = 1;
         p.out_off0 = 0; p.taps = ksize; p.tap_off0 = -(ksize - 1) / 2 * dilation; p.tap_step = dilation;
         TcLaunch Lc;
-        rc = tc_prepare(Lc, a, B, L, ci_pad, wp, n_pad, p);
+        rc = tc_prepare(Lc, fmt, a, B, L, ci_pad, wp, n_pad, p);
         if (!rc) rc = tc_launch(Lc, st);
     }
     if (!rc) rc = launch_cl_to_cf_f32(ox, y, B, cout, L, st);
-    if (!rc && y_act) rc = launch_cl_bf16_to_cf_f32(oa, y_act, B, cout, L, cout, st);
+    if (!rc && y_act) rc = launch_cl_16_to_cf_f32(oa, y_act, B, cout, L, cout, fmt, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(a); cudaFree(wp); cudaFree(oa); cudaFree(ox); cudaFree(rcl);
     if (!rc && e != cudaSuccess) return set_error(VTTS_E_CUDA, "vtts_dbg_conv1d_tc: %s", cudaGetErrorString(e));

@@ -24,8 +24,8 @@ int set_error(int code, const char *fmt, ...) {
 static int convT_out_len(int L, int s, int k, int p, int op) { return (L - 1) * s - 2 * p + k + op; }
 
 static void free_layer(Layer &l) {
-    cudaFree(l.w_fold); cudaFree(l.w_f32); cudaFree(l.bias); cudaFree(l.w_bf16); cudaFree(l.w_aux);
-    l.w_fold = l.w_f32 = l.bias = l.w_aux = nullptr; l.w_bf16 = nullptr;
+    cudaFree(l.w_fold); cudaFree(l.w_f32); cudaFree(l.bias); cudaFree(l.w16[0]); cudaFree(l.w16[1]); cudaFree(l.w_aux);
+    l.w_fold = l.w_f32 = l.bias = l.w_aux = nullptr; l.w16[0] = l.w16[1] = nullptr;
 }
 
 }  // namespace vtts
@@ -292,7 +292,7 @@ extern "C" int vtts_gen_workspace_bytes(const VttsGen *h, int B, int T, int prec
         *bytes = 5 * align_up(plan.max_elems * sizeof(float), 256) + align_up((size_t)B * h->cfg.channels * sizeof(float), 256);
         return VTTS_OK;
     }
-    if (precision == VTTS_PRECISION_BF16) return tc_workspace_bytes(h, B, T, bytes);
+    if (precision == VTTS_PRECISION_BF16 || precision == VTTS_PRECISION_FP16) return tc_workspace_bytes(h, B, T, bytes);
     return set_error(VTTS_E_INVALID, "vtts_gen_workspace_bytes: unknown precision %d", precision);
 }
 
@@ -306,8 +306,9 @@ extern "C" int vtts_gen_forward(VttsGen *h, const float *c, const float *g, floa
     h->launch_count = 0;
     if (precision == VTTS_PRECISION_FP32)
         return forward_fp32(h, c, g, wav, B, T, workspace, workspace_bytes, dump_stage, dump_out, (cudaStream_t)stream);
-    if (precision == VTTS_PRECISION_BF16)
-        return tc_forward(h, c, g, wav, B, T, workspace, workspace_bytes, dump_stage, dump_out, (cudaStream_t)stream);
+    if (precision == VTTS_PRECISION_BF16 || precision == VTTS_PRECISION_FP16)
+        return tc_forward(h, precision == VTTS_PRECISION_BF16 ? VTTS_FMT_BF16 : VTTS_FMT_FP16, c, g, wav, B, T, workspace,
+                          workspace_bytes, dump_stage, dump_out, (cudaStream_t)stream);
     return set_error(VTTS_E_INVALID, "vtts_gen_forward: unknown precision %d", precision);
 }
 

@@ -13,7 +13,7 @@ struct Layer {
     float *w_fold = nullptr; // folded fp32 weight, reference layout
     float *w_f32 = nullptr;  // fp32 packed [phase][ci][tap][co]
     float *bias = nullptr;   // fp32 (cout) or null
-    __nv_bfloat16 *w_bf16 = nullptr;  // tcgen05 packing [tap][n][ci_pad] (conv_tc.cu)
+    uint16_t *w16[2] = {nullptr, nullptr};  // tcgen05 packing [tap][n_pad][ci_pad], [0] bf16 / [1] fp16 (conv_tc.cu)
     float *w_aux = nullptr;  // output conv only: fp32 [oc][k][ci] for the channels-last kernel
     int ci_pad = 0;          // bf16 packing: padded input channels
     int n_total = 0;         // bf16 packing: rows per tap (cout, or s*cout for polyphase)
@@ -45,7 +45,7 @@ namespace vtts {
 // tcgen05 path (conv_tc.cu)
 int tc_pack_layer(VttsGen *h, int layer, cudaStream_t stream);
 int tc_workspace_bytes(const VttsGen *h, int B, int T, size_t *bytes);
-int tc_forward(VttsGen *h, const float *c, const float *g, float *wav, int B, int T,
+int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, int B, int T,
                void *workspace, size_t workspace_bytes, int dump_stage, float *dump_out,
                cudaStream_t stream);
 void tc_destroy(VttsGen *h);

@@ -92,13 +92,13 @@ int launch_pack_convT_fp32(const float *w, float *packed, int cin, int cout, int
 
 // ---------------------------------------------------------------------------------------------
 // layout conversion through a 32x32 shared-memory transpose tile
-// (B, C, L) fp32 -> (B, L, Cpad) bf16 with LeakyReLU(slope) fused, zero channel padding
-__global__ void cf_to_cl_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y,
-                                     int C, int L, int Cpad, float slope) {
+// (B, C, L) fp32 -> (B, L, Cpad) bf16/fp16 with LeakyReLU(slope) fused, zero channel padding
+__global__ void cf_to_cl_16_kernel(const float *__restrict__ x, uint16_t *__restrict__ y,
+                                   int C, int L, int Cpad, float slope, int fmt) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float *xb = x + (size_t)b * C * L;
-    __nv_bfloat16 *yb = y + (size_t)b * L * Cpad;
+    uint16_t *yb = y + (size_t)b * L * Cpad;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int c = c0 + r, l = l0 + threadIdx.x;
         tile[r][threadIdx.x] = (c < C && l < L) ? xb[(size_t)c * L + l] : 0.f;
@@ -106,14 +106,14 @@ __global__ void cf_to_cl_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int l = l0 + r, c = c0 + threadIdx.x;
-        if (l < L && c < Cpad) yb[(size_t)l * Cpad + c] = __float2bfloat16(lrelu(tile[threadIdx.x][r], slope));
+        if (l < L && c < Cpad) yb[(size_t)l * Cpad + c] = cvt16(lrelu(tile[threadIdx.x][r], slope), fmt);
     }
 }
 
-int launch_cf_to_cl_bf16(const float *x, __nv_bfloat16 *y, int B, int C, int L, int Cpad,
-                         float slope, cudaStream_t stream) {
+int launch_cf_to_cl_16(const float *x, uint16_t *y, int B, int C, int L, int Cpad, float slope, int fmt,
+                       cudaStream_t stream) {
     dim3 grid((unsigned)ceil_div(L, 32), (unsigned)ceil_div(Cpad, 32), (unsigned)B);
-    cf_to_cl_bf16_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, y, C, L, Cpad, slope);
+    cf_to_cl_16_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, y, C, L, Cpad, slope, fmt);
     VTTS_CHECK_LAUNCH();
     return VTTS_OK;
 }
@@ -142,16 +142,16 @@ int launch_cl_to_cf_f32(const float *x, float *y, int B, int C, int L, cudaStrea
     return VTTS_OK;
 }
 
-// (B, L, Cld) bf16 (first C channels) -> (B, C, L) fp32
-__global__ void cl_bf16_to_cf_f32_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y,
-                                         int C, int L, int Cld) {
+// (B, L, Cld) 16-bit (first C channels) -> (B, C, L) fp32
+__global__ void cl_16_to_cf_f32_kernel(const uint16_t *__restrict__ x, float *__restrict__ y,
+                                       int C, int L, int Cld, int fmt) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const __nv_bfloat16 *xb = x + (size_t)b * Cld * L;
+    const uint16_t *xb = x + (size_t)b * Cld * L;
     float *yb = y + (size_t)b * C * L;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int l = l0 + r, c = c0 + threadIdx.x;
-        tile[r][threadIdx.x] = (c < C && l < L) ? __bfloat162float(xb[(size_t)l * Cld + c]) : 0.f;
+        tile[r][threadIdx.x] = (c < C && l < L) ? cvt16_to_f32(xb[(size_t)l * Cld + c], fmt) : 0.f;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -160,10 +160,10 @@ __global__ void cl_bf16_to_cf_f32_kernel(const __nv_bfloat16 *__restrict__ x, fl
     }
 }
 
-int launch_cl_bf16_to_cf_f32(const __nv_bfloat16 *x, float *y, int B, int C, int L, int Cld,
-                             cudaStream_t stream) {
+int launch_cl_16_to_cf_f32(const uint16_t *x, float *y, int B, int C, int L, int Cld, int fmt,
+                           cudaStream_t stream) {
     dim3 grid((unsigned)ceil_div(L, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
-    cl_bf16_to_cf_f32_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, y, C, L, Cld);
+    cl_16_to_cf_f32_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, y, C, L, Cld, fmt);
     VTTS_CHECK_LAUNCH();
     return VTTS_OK;
 }

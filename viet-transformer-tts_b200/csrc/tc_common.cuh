@@ -120,14 +120,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 // ---- descriptors ---------------------------------------------------------------------------------
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4)                     // c_format = F32
-           | (1u << 7)                   // a_format = BF16
-           | (1u << 10)                  // b_format = BF16
-           | ((uint32_t)(N >> 3) << 17)  // n_dim
-           | ((uint32_t)(M >> 4) << 24); // m_dim
+// Instruction descriptor, kind::f16: 16-bit x 16-bit -> fp32, both operands K-major.
+// fmt: 0 = bf16 operands, 1 = fp16 operands (same tensor-core rate; fp16 has 3 more mantissa bits).
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int fmt) {
+    return (1u << 4)                                  // c_format = F32
+           | ((fmt == 0 ? 1u : 0u) << 7)              // a_format: 1 = BF16, 0 = F16
+           | ((fmt == 0 ? 1u : 0u) << 10)             // b_format
+           | ((uint32_t)(N >> 3) << 17)               // n_dim
+           | ((uint32_t)(M >> 4) << 24);              // m_dim
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return make_idesc_16(M, N, 0); }
 // Shared-memory matrix descriptor, K-major, swizzled rows of `row_bytes` (128 -> SW128, 64 -> SW64).
 // Rows are stored at a pitch of row_bytes; 8-row swizzle atoms are contiguous (SBO = 8 * row_bytes).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int row_bytes, uint32_t base_offset) {
@@ -149,7 +151,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 
-// bf16 tensor, `rank` dims (dim 0 innermost/contiguous), zero OOB fill.
+// 16-bit element tensor (bf16 or fp16: moved as opaque 16-bit words), `rank` dims
+// (dim 0 innermost/contiguous), zero OOB fill.
 int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                    const uint32_t *box, int swizzle_bytes);
 
