@@ -79,8 +79,6 @@ constexpr int TM = 128;            // output rows per tile (UMMA M, TMEM lanes)
 constexpr int HALO_MAX = 64;       // (k-1)*d <= 64
 constexpr int ACT_ROWS = TN + HALO_MAX;
 constexpr int BOX_ROWS = 64;       // activation TMA box height
-constexpr int ACT_STAGES = 2;      // activation tiles in flight (one per K chunk)
-constexpr int W_STAGES = 8;        // weight tiles in flight (one per (chunk, tap))
 constexpr int ACC_STAGES = 2;      // TMEM accumulators
 constexpr int PRODUCER_WARPS = 3;  // activation producer, weight producer, MMA issuer
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
@@ -106,6 +104,8 @@ struct TcConvParams {
     int out_stride, out_off0;  // t_out = i * out_stride + out_off0 + phase
     int chunks;             // K chunks (ci_pad / chunk channels)
     int taps, tap_off0, tap_step;
+    int act_stages, w_stages;  // pipeline depths (shared memory is carved at run time)
+    int w_rows;                // weight rows actually loaded per tile (<= 128; the rest of the A tile is don't-care)
     // tile schedule: tile -> (m block fastest, then time tile, then batch)
     int m_blocks, t_tiles, total_tiles;
 };
@@ -113,53 +113,55 @@ struct TcConvParams {
 // ---- epilogue helpers -------------------------------------------------------------------------------
 // max(v, v*slope) == LeakyReLU for 0 <= slope <= 1 (checked on the host); slope 1 = identity
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Fast path for one 32-column group that is entirely valid.  COUT_CT > 0: compile-time row pitch
-// (out_stride == 1, out_a_ld == cout) so every access is base + immediate.
-// MODE 0: operand copy only; MODE 1: residual + fp32 stream + operand copy; MODE 2: runtime flags.
-template <int FMT, int COUT_CT, int MODE>
+// Epilogue modes (kernel-uniform):            res  acc  div   X    A
+enum { EPI_A = 0,      //                       -    -    -    -    x   conv1 of a pair, input conv
+       EPI_RXA = 1,    //                       x    -    -    x    x   conv2 (x = xt + x), layers.py:97
+       EPI_RX = 2,     //                       x    -    -    x    -   last unit, first block (cs = ...)
+       EPI_RCX = 3,    //                       x    x    -    x    -   last unit, middle blocks (cs += ...)
+       EPI_RCDXA = 4,  //                       x    x    x    x    x   last unit, last block (c = cs / n) -> next upsample
+       EPI_RCDX = 5,   //                       x    x    x    x    -   same, last stage (fp32 output conv follows)
+       EPI_XA = 6,     //                       -    -    -    x    x   upsample
+       EPI_GENERIC = 7 };
+
+// One fully valid 32-column group.  SX_CT > 0: compile-time element pitch between time positions
+// (out_stride * cout, with out_a_ld == cout) so every access is base + immediate offset.
+template <int FMT, int SX_CT, int MODE>
 __device__ __forceinline__ void epi_group_fast(const uint32_t (&v)[32], float bias, const TcConvParams &p,
                                                long long xo, long long ao, long long sx_rt, long long sa_rt) {
-    const long long sx = COUT_CT ? (long long)COUT_CT : sx_rt;
-    const long long sa = COUT_CT ? (long long)COUT_CT : sa_rt;
-    if (MODE == 0) {
-        uint16_t *pa = p.out_a + ao;
+    constexpr bool G = MODE == EPI_GENERIC;
+    constexpr bool RES = MODE == EPI_RXA || MODE == EPI_RX || MODE == EPI_RCX || MODE == EPI_RCDXA || MODE == EPI_RCDX;
+    constexpr bool ACC = MODE == EPI_RCX || MODE == EPI_RCDXA || MODE == EPI_RCDX;
+    constexpr bool DIV = MODE == EPI_RCDXA || MODE == EPI_RCDX;
+    constexpr bool X = MODE != EPI_A;
+    constexpr bool A = MODE == EPI_A || MODE == EPI_RXA || MODE == EPI_RCDXA || MODE == EPI_XA;
+    const bool has_res = G ? (p.res != nullptr) : RES;
+    const bool has_acc = G ? (p.accumulate != 0) : ACC;
+    const bool has_div = G ? (p.divide_by > 0.f) : DIV;
+    const bool has_x = G ? (p.out_x != nullptr) : X;
+    const bool has_a = G ? (p.out_a != nullptr) : A;
+    const long long sx = SX_CT ? (long long)SX_CT : sx_rt;
+    const long long sa = SX_CT ? (long long)SX_CT : sa_rt;
+    const float *pr = p.res + xo;
+    float *px = p.out_x + xo;
+    uint16_t *pa = p.out_a + ao;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) pa[e * sa] = cvt16(lrelu_max(__uint_as_float(v[e]) + bias, p.slope_out), FMT);
-    } else if (MODE == 1) {
-        const float *pr = p.res + xo;
-        float *px = p.out_x + xo;
-        uint16_t *pa = p.out_a + ao;
+    for (int h = 0; h < 2; ++h) {
+        float rr[16], aa[16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float rr[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) rr[e] = __ldg(pr + (h * 16 + e) * sx);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float val = (__uint_as_float(v[h * 16 + e]) + bias) + rr[e];
-                px[(h * 16 + e) * sx] = val;
-                pa[(h * 16 + e) * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
-            }
+        for (int e = 0; e < 16; ++e) {
+            rr[e] = has_res ? __ldg(pr + (h * 16 + e) * sx) : 0.f;
+            aa[e] = has_acc ? px[(h * 16 + e) * sx] : 0.f;
         }
-    } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float rr[16], aa[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                rr[e] = p.res ? __ldg(p.res + xo + (h * 16 + e) * sx) : 0.f;
-                aa[e] = p.accumulate ? p.out_x[xo + (h * 16 + e) * sx] : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                float val = __uint_as_float(v[h * 16 + e]) + bias;
-                if (p.res) val = val + rr[e];
-                if (p.accumulate) val = aa[e] + val;
-                if (p.divide_by > 0.f) val = val * p.inv_div;
-                if (p.out_x) p.out_x[xo + (h * 16 + e) * sx] = val;
-                if (p.out_a) p.out_a[ao + (h * 16 + e) * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
-            }
+        for (int e = 0; e < 16; ++e) {
+            float val = __uint_as_float(v[h * 16 + e]) + bias;
+            if (has_res) val = val + rr[e];
+            if (has_acc) val = aa[e] + val;
+            if (has_div) val = val * p.inv_div;
+            if (has_x) px[(h * 16 + e) * sx] = val;
+            if (has_a) pa[(h * 16 + e) * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
         }
     }
 }
@@ -169,13 +171,13 @@ template <int FMT>
 __device__ __forceinline__ void epi_group_edge(const uint32_t (&v)[32], float bias, const TcConvParams &p, bool row_ok,
                                                int ibase0, long long t_first0, long long xo0, long long ao0,
                                                long long sx, long long sa) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
         uint32_t okmask = 0;
-        float rr[16], aa[16];
+        float rr[8], aa[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int ee = h * 16 + e;
+        for (int e = 0; e < 8; ++e) {
+            const int ee = h * 8 + e;
             const long long t = t_first0 + (long long)ee * p.out_stride;
             const bool ok = row_ok && (ibase0 + ee) < p.n_pos && t >= 0 && t < p.L_out;
             okmask |= (ok ? 1u : 0u) << e;
@@ -183,10 +185,12 @@ __device__ __forceinline__ void epi_group_edge(const uint32_t (&v)[32], float bi
             aa[e] = (ok && p.accumulate) ? p.out_x[xo0 + ee * sx] : 0.f;
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 8; ++e) {
             if (okmask & (1u << e)) {
-                const int ee = h * 16 + e;
-                float val = __uint_as_float(v[ee]) + bias;
+                const int ee = h * 8 + e;
+                // v[] must be indexed with compile-time constants (registers): select by h
+                const uint32_t bits = h == 0 ? v[e] : h == 1 ? v[8 + e] : h == 2 ? v[16 + e] : v[24 + e];
+                float val = __uint_as_float(bits) + bias;
                 if (p.res) val = val + rr[e];
                 if (p.accumulate) val = aa[e] + val;
                 if (p.divide_by > 0.f) val = val * p.inv_div;
@@ -198,19 +202,38 @@ __device__ __forceinline__ void epi_group_edge(const uint32_t (&v)[32], float bi
 }
 
 template <int FMT, int MODE>
-__device__ __forceinline__ void epi_group_dispatch(int cout_ct, const uint32_t (&v)[32], float bias,
+__device__ __forceinline__ void epi_group_stride(int sx_ct, const uint32_t (&v)[32], float bias, const TcConvParams &p,
+                                                 long long xo, long long ao, long long sx, long long sa) {
+    switch (sx_ct) {
+        case 32: epi_group_fast<FMT, 32, MODE>(v, bias, p, xo, ao, sx, sa); return;
+        case 64: epi_group_fast<FMT, 64, MODE>(v, bias, p, xo, ao, sx, sa); return;
+        case 128: epi_group_fast<FMT, 128, MODE>(v, bias, p, xo, ao, sx, sa); return;
+        case 256: epi_group_fast<FMT, 256, MODE>(v, bias, p, xo, ao, sx, sa); return;
+        default: epi_group_fast<FMT, 0, MODE>(v, bias, p, xo, ao, sx, sa); return;
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void epi_group_dispatch(int mode, int sx_ct, const uint32_t (&v)[32], float bias,
                                                    const TcConvParams &p, long long xo, long long ao, long long sx,
                                                    long long sa) {
-    if (MODE != 2) {
-        switch (cout_ct) {
-            case 32: epi_group_fast<FMT, 32, MODE>(v, bias, p, xo, ao, sx, sa); return;
-            case 64: epi_group_fast<FMT, 64, MODE>(v, bias, p, xo, ao, sx, sa); return;
-            case 128: epi_group_fast<FMT, 128, MODE>(v, bias, p, xo, ao, sx, sa); return;
-            case 256: epi_group_fast<FMT, 256, MODE>(v, bias, p, xo, ao, sx, sa); return;
-            default: break;
-        }
+    switch (mode) {
+        case EPI_A: epi_group_stride<FMT, EPI_A>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
+        case EPI_RXA: epi_group_stride<FMT, EPI_RXA>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
+        case EPI_RX: epi_group_stride<FMT, EPI_RX>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
+        case EPI_RCX: epi_group_stride<FMT, EPI_RCX>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
+        case EPI_RCDXA: epi_group_stride<FMT, EPI_RCDXA>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
+        case EPI_RCDX: epi_group_stride<FMT, EPI_RCDX>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
+        case EPI_XA:   // upsample: pitches s*cout are 64 / 128 / 1024 / 2048 for V1
+            switch (sx_ct) {
+                case 64: epi_group_fast<FMT, 64, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
+                case 128: epi_group_fast<FMT, 128, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
+                case 1024: epi_group_fast<FMT, 1024, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
+                case 2048: epi_group_fast<FMT, 2048, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
+                default: epi_group_fast<FMT, 0, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
+            }
+        default: epi_group_fast<FMT, 0, EPI_GENERIC>(v, bias, p, xo, ao, sx, sa); return;
     }
-    epi_group_fast<FMT, 0, MODE>(v, bias, p, xo, ao, sx, sa);
 }
 
 // ROWB: bytes per operand row: 128 (64 channels, SW128) or 64 (32 channels, SW64); FMT: 0 bf16, 1 fp16
@@ -229,6 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         __trap();
     }
     uint8_t *s_act = smem;
+    const uint32_t ACT_STAGES = (uint32_t)p.act_stages, W_STAGES = (uint32_t)p.w_stages;
     uint8_t *s_w = smem + (size_t)ACT_STAGES * ACT_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + (size_t)W_STAGES * W_BYTES);
     uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
@@ -243,8 +267,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
-        for (int s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
+        for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
         fence_barrier_init();
     }
@@ -286,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     for (int j = 0; j < p.taps; ++j, ++it) {
                         const uint32_t s = it % W_STAGES, ph = (it / W_STAGES) & 1u;
                         mbar_wait(&w_empty[s], ph ^ 1u);
-                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)W_BYTES);
+                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB));
                         tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
                     }
             }
@@ -334,11 +358,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const long long sx = (long long)p.out_stride * p.cout;      // fp32 elements between time positions
         const long long sa = (long long)p.out_stride * p.out_a_ld;  // 16-bit elements between time positions
         // kernel-uniform epilogue specialisation
-        const bool plain = !p.accumulate && p.divide_by <= 0.f;
-        const int mode = (plain && !p.res && !p.out_x && p.out_a) ? 0 : (plain && p.res && p.out_x && p.out_a) ? 1 : 2;
-        const int cout_ct = (p.out_stride == 1 && p.out_a_ld == p.cout) ? p.cout : 0;
+        const bool R = p.res != nullptr, C = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
+                   A = p.out_a != nullptr;
+        const int mode = (!R && !C && !D && !X && A) ? EPI_A
+                       : (R && !C && !D && X && A) ? EPI_RXA
+                       : (R && !C && !D && X && !A) ? EPI_RX
+                       : (R && C && !D && X && !A) ? EPI_RCX
+                       : (R && C && D && X && A) ? EPI_RCDXA
+                       : (R && C && D && X && !A) ? EPI_RCDX
+                       : (!R && !C && !D && X && A) ? EPI_XA : EPI_GENERIC;
+        const int sx_ct = (!A || p.out_a_ld == p.cout) ? (int)sx : 0;
+        // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one
+        // tile ahead and spread over all epilogue threads: turns the per-group HBM round trips of
+        // the (few) active warps into L2 hits.  Only for unit-stride layers (upsamples read neither).
+        const int et = threadIdx.x - PRODUCER_WARPS * 32;          // 0 .. EPI_WARPS*32-1
+        auto prefetch_tile = [&](int tile) {
+            if (!(R || C) || p.out_stride != 1) return;
+            const int n0p = (tile % p.m_blocks) * TM;
+            const int restp = tile / p.m_blocks;
+            const int i0p = (restp % p.t_tiles) * TN, bp = restp / p.t_tiles;
+            const int rows_ch = (p.n_total - n0p) < TM ? (p.n_total - n0p) : TM;   // channels of this m-block
+            const int lines_per_row = (rows_ch * 4 + 127) / 128;
+            const int n_lines = TN * lines_per_row;
+            for (int l = et; l < n_lines; l += EPI_WARPS * 32) {
+                const int row = l / lines_per_row, seg = l - row * lines_per_row;
+                const int t = i0p + row;
+                if (t < p.n_pos && t < p.L_out) {
+                    const long long off = ((long long)bp * p.L_out + t) * p.cout + n0p + seg * 32;
+                    if (R) prefetch_l2(p.res + off);
+                    if (C) prefetch_l2(p.out_x + off);
+                }
+            }
+        };
+        if ((int)blockIdx.x < p.total_tiles) prefetch_tile(blockIdx.x);
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            if (tile + (int)gridDim.x < p.total_tiles) prefetch_tile(tile + gridDim.x);
             const int n0 = (tile % p.m_blocks) * TM;
             const int rest = tile / p.m_blocks;
             const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
@@ -370,9 +425,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     const long long ao = row0 * p.out_a_ld + co;
                     const bool full = rows_full && (ibase + 32 <= p.n_pos) && t_first >= 0 && t_last < p.L_out;
                     if (full) {
-                        if (mode == 0) epi_group_dispatch<FMT, 0>(cout_ct, v, bias, p, xo, ao, sx, sa);
-                        else if (mode == 1) epi_group_dispatch<FMT, 1>(cout_ct, v, bias, p, xo, ao, sx, sa);
-                        else epi_group_dispatch<FMT, 2>(cout_ct, v, bias, p, xo, ao, sx, sa);
+                        epi_group_dispatch<FMT>(mode, sx_ct, v, bias, p, xo, ao, sx, sa);
                     } else {
                         epi_group_edge<FMT>(v, bias, p, row_ok, ibase, t_first, xo, ao, sx, sa);
                     }
@@ -397,9 +450,9 @@ struct TcLaunch {
     size_t smem;
 };
 
-static size_t tc_smem_bytes(int rowb) {
-    return (size_t)ACT_STAGES * ACT_ROWS * rowb + (size_t)W_STAGES * TM * rowb +
-           (size_t)(2 * ACT_STAGES + 2 * W_STAGES + 2 * ACC_STAGES) * 8 + 16;
+static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
+    return (size_t)act_stages * ACT_ROWS * rowb + (size_t)w_stages * TM * rowb +
+           (size_t)(2 * act_stages + 2 * w_stages + 2 * ACC_STAGES) * 8 + 16;
 }
 
 static int tc_num_sms() {
@@ -451,8 +504,15 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     const long long total = (long long)p.m_blocks * p.t_tiles * B;
     if (total > 0x7fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "tc: too many tiles");
     p.total_tiles = (int)total;
+    // pipeline depths: narrow (HBM-bound) layers need many activation bytes in flight, wide
+    // (tensor-bound) layers a deep weight pipeline
+    if (rowb == 64) { p.act_stages = 6; p.w_stages = 8; }
+    else if (p.chunks == 1) { p.act_stages = 4; p.w_stages = 4; }
+    else { p.act_stages = 3; p.w_stages = 6; }
+    p.w_rows = p.n_total >= TM ? TM : ((p.n_total + 31) / 32) * 32;
     L.p = p;
-    L.smem = tc_smem_bytes(rowb);
+    L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
+    if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc: %zu B shared memory", L.smem);
     const int sms = tc_num_sms();
     L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     {
@@ -465,7 +525,7 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     {
         uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)n_pad, (uint64_t)p.taps};
         uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)n_pad};
-        uint32_t box[3] = {(uint32_t)ch, TM, 1};
+        uint32_t box[3] = {(uint32_t)ch, (uint32_t)p.w_rows, 1};
         int rc = make_tmap_bf16(&L.tm_w, w, 3, dims, str, box, rowb);
         if (rc) return rc;
     }
