@@ -508,7 +508,7 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     // (tensor-bound) layers a deep weight pipeline
     if (rowb == 64) { p.act_stages = 6; p.w_stages = 8; }
     else if (p.chunks == 1) { p.act_stages = 4; p.w_stages = 4; }
-    else { p.act_stages = 3; p.w_stages = 6; }
+    else { p.act_stages = 2; p.w_stages = 8; }
     p.w_rows = p.n_total >= TM ? TM : ((p.n_total + 31) / 32) * 32;
     L.p = p;
     L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
