@@ -106,6 +106,7 @@ struct TcConvParams {
     int taps, tap_off0, tap_step;
     int act_stages, w_stages;  // pipeline depths (shared memory is carved at run time)
     int w_rows;                // weight rows actually loaded per tile (<= 128; the rest of the A tile is don't-care)
+    int epi_quarters;          // TMEM lane quarters holding real output rows in EVERY tile (1..4)
     // tile schedule: tile -> (m block fastest, then time tile, then batch)
     int m_blocks, t_tiles, total_tiles;
 };
@@ -269,7 +270,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
         for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], (uint32_t)(p.epi_quarters * (EPI_WARPS / 4)));  // one arrival per participating warp
+        }
         fence_barrier_init();
     }
     if (warp == 2) {  // MMA warp owns the TMEM allocation (all 512 columns: 2 accumulators)
@@ -394,6 +398,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
             if (tile + (int)gridDim.x < p.total_tiles) prefetch_tile(tile + gridDim.x);
+            if (quarter >= p.epi_quarters) continue;        // this warp's TMEM lanes never hold real rows: prefetch duty only
             const int n0 = (tile % p.m_blocks) * TM;
             const int rest = tile / p.m_blocks;
             const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
@@ -408,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
             const bool quarter_used = nq < p.n_total;       // warp-uniform
             const bool rows_full = nq + 32 <= p.n_total;    // warp-uniform
-            mbar_wait(&acc_full[buf], (tl / ACC_STAGES) & 1u);
+            mbar_wait_relaxed(&acc_full[buf], (tl / ACC_STAGES) & 1u);
             tc_fence_after();
             if (quarter_used) {
                 for (int cg = 0; cg < COLS_PER; cg += 32) {
@@ -510,6 +515,8 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     else if (p.chunks == 1) { p.act_stages = 4; p.w_stages = 4; }
     else { p.act_stages = 2; p.w_stages = 8; }
     p.w_rows = p.n_total >= TM ? TM : ((p.n_total + 31) / 32) * 32;
+    // quarters that hold real rows in every tile (a partial last m-block keeps all warps in the handshake)
+    p.epi_quarters = (p.m_blocks == 1 && p.n_total < TM) ? (p.n_total + 31) / 32 : 4;
     L.p = p;
     L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc: %zu B shared memory", L.smem);
