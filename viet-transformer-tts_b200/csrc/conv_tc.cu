@@ -82,6 +82,11 @@ constexpr int BOX_ROWS = 64;       // activation TMA box height
 constexpr int ACC_STAGES = 2;      // TMEM accumulators
 constexpr int PRODUCER_WARPS = 3;  // activation producer, weight producer, MMA issuer
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
+
+// debug trace (vtts_dbg_trace_*): 16 stamps per tile for the first TRACE_TILES tiles of block 0
+constexpr int TRACE_TILES = 64;
+__device__ long long g_trace[TRACE_TILES * 16];
+#define VTTS_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && tl < TRACE_TILES) g_trace[tl * 16 + (slot)] = clock64(); } while (0)
 constexpr int TC_THREADS = (PRODUCER_WARPS + EPI_WARPS) * 32;
 
 struct TcConvParams {
@@ -107,6 +112,7 @@ struct TcConvParams {
     int act_stages, w_stages;  // pipeline depths (shared memory is carved at run time)
     int w_rows;                // weight rows actually loaded per tile (<= 128; the rest of the A tile is don't-care)
     int epi_quarters;          // TMEM lane quarters holding real output rows in EVERY tile (1..4)
+    int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
     // tile schedule: tile -> (m block fastest, then time tile, then batch)
     int m_blocks, t_tiles, total_tiles;
 };
@@ -289,13 +295,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
                 const int rest = tile / p.m_blocks;
                 const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
                 for (int c = 0; c < p.chunks; ++c, ++it) {
                     const uint32_t s = it % ACT_STAGES, ph = (it / ACT_STAGES) & 1u;
+                    if (c == 0) VTTS_TRACE(4);
                     mbar_wait(&act_empty[s], ph ^ 1u);
+                    if (c == 0) VTTS_TRACE(5);
                     mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
                     for (int bx = 0; bx < nbox; ++bx)
                         tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act,
@@ -307,13 +315,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ===== weight producer: one 128-row tile per (chunk, tap) =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_w);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
                 const int n0 = (tile % p.m_blocks) * TM;
                 for (int c = 0; c < p.chunks; ++c)
                     for (int j = 0; j < p.taps; ++j, ++it) {
                         const uint32_t s = it % W_STAGES, ph = (it / W_STAGES) & 1u;
+                        if ((c | j) == 0) VTTS_TRACE(6);
                         mbar_wait(&w_empty[s], ph ^ 1u);
+                        if ((c | j) == 0) VTTS_TRACE(7);
                         mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB));
                         tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
                     }
@@ -326,12 +336,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             uint32_t ia = 0, iw = 0, tl = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
+                VTTS_TRACE(0);
                 mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
+                VTTS_TRACE(1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * TN;
                 for (int c = 0; c < p.chunks; ++c, ++ia) {
                     const uint32_t sa = ia % ACT_STAGES;
                     mbar_wait(&act_full[sa], (ia / ACT_STAGES) & 1u);
+                    if (c == 0) VTTS_TRACE(2);
                     const uint32_t act_base = smem_u32(s_act + (size_t)sa * ACT_BYTES);
                     for (int j = 0; j < p.taps; ++j, ++iw) {
                         const uint32_t sw = iw % W_STAGES;
@@ -349,6 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     }
                     umma_commit(&act_empty[sa]);     // activation stage reusable
                 }
+                VTTS_TRACE(3);
                 umma_commit(&acc_full[buf]);         // accumulator complete -> epilogue
             }
         }
@@ -413,7 +427,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
             const bool quarter_used = nq < p.n_total;       // warp-uniform
             const bool rows_full = nq + 32 <= p.n_total;    // warp-uniform
+            if (ew == 1 && lane == 0) VTTS_TRACE(8);
             mbar_wait_relaxed(&acc_full[buf], (tl / ACC_STAGES) & 1u);
+            if (ew == 1 && lane == 0) VTTS_TRACE(9);
             tc_fence_after();
             if (quarter_used) {
                 for (int cg = 0; cg < COLS_PER; cg += 32) {
@@ -436,6 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     }
                 }
             }
+            if (ew == 1 && lane == 0) VTTS_TRACE(10);
             // all of this warp's tcgen05.ld have completed (wait::ld above): release the accumulator
             tc_fence_before();
             __syncwarp();
@@ -1009,6 +1026,17 @@ extern "C" int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float 
     return VTTS_OK;
 }
 
+static int g_trace_on = 0;
+extern "C" int vtts_dbg_trace(int enable, long long *host_out, int n) {
+    g_trace_on = enable;
+    if (host_out && n > 0) {
+        if (n > TRACE_TILES * 16) n = TRACE_TILES * 16;
+        VTTS_CHECK_CUDA(cudaDeviceSynchronize());
+        VTTS_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * n));
+    }
+    return VTTS_OK;
+}
+
 // Single Conv1d layer through the tensor-core kernel, channels-first fp32 in/out (test hook).
 extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const float *res, float *y,
                                   float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
@@ -1038,6 +1066,7 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
         p.bias = bias; p.res = res ? rcl : nullptr; p.out_x = ox; p.out_a = y_act ? oa : nullptr; p.out_a_ld = cout;
         p.slope_out = slope_out; p.n_total = cout; p.cout = cout; p.L_out = L; p.n_pos = L; p.out_stride = 1;
         p.out_off0 = 0; p.taps = ksize; p.tap_off0 = -(ksize - 1) / 2 * dilation; p.tap_step = dilation;
+        p.trace = g_trace_on;
         TcLaunch Lc;
         rc = tc_prepare(Lc, fmt, a, B, L, ci_pad, wp, n_pad, p);
         if (!rc) rc = tc_launch(Lc, st);
