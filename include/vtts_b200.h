@@ -164,6 +164,10 @@ int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const 
                        float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
                        float slope_in, float slope_out, int fp16, vtts_stream_t stream);
 
+/* Debug: enable per-tile clock64() tracing in vtts_dbg_conv1d_tc (block 0) and/or read the trace
+ * buffer (16 stamps per tile, first 64 tiles) back to host memory. */
+int vtts_dbg_trace(int enable, long long *host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif
