@@ -112,15 +112,24 @@ struct TcConvParams {
     int act_stages, w_stages;  // pipeline depths (shared memory is carved at run time)
     int w_rows;                // weight rows actually loaded per tile (<= 128; the rest of the A tile is don't-care)
     int epi_quarters;          // TMEM lane quarters holding real output rows in EVERY tile (1..4)
+    int rep;                   // weight rows replicated `rep` times across the 128 lanes (narrow layers: 128 / n_total)
+    int L4;                    // ceil(L_out / 4): fp32 streams are stored time-packed [b][t/4][c][4]
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
     // tile schedule: tile -> (m block fastest, then time tile, then batch)
     int m_blocks, t_tiles, total_tiles;
 };
 
 // ---- epilogue helpers -------------------------------------------------------------------------------
+// fp32 streams (residual x, MRF sum) use a time-packed layout [b][t/4][c][4]: a thread (one channel)
+// owns 4 consecutive time steps = 16 bytes, consecutive lanes (channels) are 16 bytes apart, so a
+// warp's 128-bit access covers 512 contiguous bytes.  The 16-bit operand copy stays [b][t][c]
+// (K-major rows for TMA).
 // max(v, v*slope) == LeakyReLU for 0 <= slope <= 1 (checked on the host); slope 1 = identity
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ long long tp4_off(long long b, long long L4, long long t, int C, int c) {
+    return ((b * L4 + (t >> 2)) * C + c) * 4 + (t & 3);
+}
 
 // Epilogue modes (kernel-uniform):            res  acc  div   X    A
 enum { EPI_A = 0,      //                       -    -    -    -    x   conv1 of a pair, input conv
@@ -129,117 +138,94 @@ enum { EPI_A = 0,      //                       -    -    -    -    x   conv1 of
        EPI_RCX = 3,    //                       x    x    -    x    -   last unit, middle blocks (cs += ...)
        EPI_RCDXA = 4,  //                       x    x    x    x    x   last unit, last block (c = cs / n) -> next upsample
        EPI_RCDX = 5,   //                       x    x    x    x    -   same, last stage (fp32 output conv follows)
-       EPI_XA = 6,     //                       -    -    -    x    x   upsample
-       EPI_GENERIC = 7 };
+       EPI_GENERIC = 6 };
+template <int MODE> struct EpiFlags {
+    static constexpr bool RES = MODE >= EPI_RXA && MODE <= EPI_RCDX;
+    static constexpr bool ACC = MODE == EPI_RCX || MODE == EPI_RCDXA || MODE == EPI_RCDX;
+    static constexpr bool DIV = MODE == EPI_RCDXA || MODE == EPI_RCDX;
+    static constexpr bool X = MODE != EPI_A;
+    static constexpr bool A = MODE == EPI_A || MODE == EPI_RXA || MODE == EPI_RCDXA;
+};
 
-// One fully valid 32-column group.  SX_CT > 0: compile-time element pitch between time positions
-// (out_stride * cout, with out_a_ld == cout) so every access is base + immediate offset.
-template <int FMT, int SX_CT, int MODE>
-__device__ __forceinline__ void epi_group_fast(const uint32_t (&v)[32], float bias, const TcConvParams &p,
-                                               long long xo, long long ao, long long sx_rt, long long sa_rt) {
-    constexpr bool G = MODE == EPI_GENERIC;
-    constexpr bool RES = MODE == EPI_RXA || MODE == EPI_RX || MODE == EPI_RCX || MODE == EPI_RCDXA || MODE == EPI_RCDX;
-    constexpr bool ACC = MODE == EPI_RCX || MODE == EPI_RCDXA || MODE == EPI_RCDX;
-    constexpr bool DIV = MODE == EPI_RCDXA || MODE == EPI_RCDX;
-    constexpr bool X = MODE != EPI_A;
-    constexpr bool A = MODE == EPI_A || MODE == EPI_RXA || MODE == EPI_RCDXA || MODE == EPI_XA;
-    const bool has_res = G ? (p.res != nullptr) : RES;
-    const bool has_acc = G ? (p.accumulate != 0) : ACC;
-    const bool has_div = G ? (p.divide_by > 0.f) : DIV;
-    const bool has_x = G ? (p.out_x != nullptr) : X;
-    const bool has_a = G ? (p.out_a != nullptr) : A;
-    const long long sx = SX_CT ? (long long)SX_CT : sx_rt;
-    const long long sa = SX_CT ? (long long)SX_CT : sa_rt;
-    const float *pr = p.res + xo;
-    float *px = p.out_x + xo;
-    uint16_t *pa = p.out_a + ao;
+// residual (and running-sum) values of one 16-column group: 4 x 128-bit loads per stream
+struct EpiLoads { float4 r[4]; };
+template <int C_CT>
+__device__ __forceinline__ void epi_load16(EpiLoads &d, const float *base, int C_rt) {
+    const int C = C_CT ? C_CT : C_rt;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float rr[16], aa[16];
+    for (int m = 0; m < 4; ++m) d.r[m] = __ldg(reinterpret_cast<const float4 *>(base + (size_t)m * C * 4));
+}
+
+// One fully valid 16-column group of a unit-stride layer.  C_CT > 0: compile-time channel count.
+template <int FMT, int C_CT, int MODE>
+__device__ __forceinline__ void epi_group16(const uint32_t (&v)[16], float bias, const TcConvParams &p,
+                                            const EpiLoads &res, float *px /* tp4 base */, uint16_t *pa /* [t][c] base */) {
+    using F = EpiFlags<MODE>;
+    const int C = C_CT ? C_CT : p.cout;
+    const int lda = C_CT ? C_CT : p.out_a_ld;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            rr[e] = has_res ? __ldg(pr + (h * 16 + e) * sx) : 0.f;
-            aa[e] = has_acc ? px[(h * 16 + e) * sx] : 0.f;
+    for (int m = 0; m < 4; ++m) {
+        float val[4];
+        const float rr[4] = {res.r[m].x, res.r[m].y, res.r[m].z, res.r[m].w};
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (F::ACC) acc4 = *reinterpret_cast<const float4 *>(px + (size_t)m * C * 4);
+        const float aa[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            float x = __uint_as_float(v[m * 4 + d]) + bias;
+            if (F::RES) x = x + rr[d];
+            if (F::ACC) x = aa[d] + x;
+            if (F::DIV) x = x * p.inv_div;
+            val[d] = x;
         }
+        if (F::X) *reinterpret_cast<float4 *>(px + (size_t)m * C * 4) = make_float4(val[0], val[1], val[2], val[3]);
+        if (F::A) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            float val = __uint_as_float(v[h * 16 + e]) + bias;
-            if (has_res) val = val + rr[e];
-            if (has_acc) val = aa[e] + val;
-            if (has_div) val = val * p.inv_div;
-            if (has_x) px[(h * 16 + e) * sx] = val;
-            if (has_a) pa[(h * 16 + e) * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
+            for (int d = 0; d < 4; ++d) pa[(size_t)(m * 4 + d) * lda] = cvt16(lrelu_max(val[d], p.slope_out), FMT);
         }
     }
 }
 
-// Generic path: per-element validity (tile edges, polyphase output bounds, padded rows).
+// Generic path: per-element validity and addressing (tile edges, polyphase upsample outputs, padded rows).
 template <int FMT>
-__device__ __forceinline__ void epi_group_edge(const uint32_t (&v)[32], float bias, const TcConvParams &p, bool row_ok,
-                                               int ibase0, long long t_first0, long long xo0, long long ao0,
-                                               long long sx, long long sa) {
-#pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
-        uint32_t okmask = 0;
-        float rr[8], aa[8];
+__device__ __forceinline__ void epi_group16_edge(const uint32_t (&v)[16], float bias, const TcConvParams &p, bool row_ok,
+                                                 int b, int ibase, int phase, int co) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int ee = h * 8 + e;
-            const long long t = t_first0 + (long long)ee * p.out_stride;
-            const bool ok = row_ok && (ibase0 + ee) < p.n_pos && t >= 0 && t < p.L_out;
-            okmask |= (ok ? 1u : 0u) << e;
-            rr[e] = (ok && p.res) ? __ldg(p.res + xo0 + ee * sx) : 0.f;
-            aa[e] = (ok && p.accumulate) ? p.out_x[xo0 + ee * sx] : 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (okmask & (1u << e)) {
-                const int ee = h * 8 + e;
-                // v[] must be indexed with compile-time constants (registers): select by h
-                const uint32_t bits = h == 0 ? v[e] : h == 1 ? v[8 + e] : h == 2 ? v[16 + e] : v[24 + e];
-                float val = __uint_as_float(bits) + bias;
-                if (p.res) val = val + rr[e];
-                if (p.accumulate) val = aa[e] + val;
-                if (p.divide_by > 0.f) val = val * p.inv_div;
-                if (p.out_x) p.out_x[xo0 + ee * sx] = val;
-                if (p.out_a) p.out_a[ao0 + ee * sa] = cvt16(lrelu_max(val, p.slope_out), FMT);
-            }
+    for (int e = 0; e < 16; ++e) {
+        const long long t = (long long)(ibase + e) * p.out_stride + p.out_off0 + phase;
+        if (row_ok && (ibase + e) < p.n_pos && t >= 0 && t < p.L_out) {
+            const long long xo = tp4_off(b, p.L4, t, p.cout, co);
+            float val = __uint_as_float(v[e]) + bias;
+            if (p.res) val = val + __ldg(p.res + xo);
+            if (p.accumulate) val = p.out_x[xo] + val;
+            if (p.divide_by > 0.f) val = val * p.inv_div;
+            if (p.out_x) p.out_x[xo] = val;
+            if (p.out_a) p.out_a[((long long)b * p.L_out + t) * p.out_a_ld + co] = cvt16(lrelu_max(val, p.slope_out), FMT);
         }
     }
 }
 
 template <int FMT, int MODE>
-__device__ __forceinline__ void epi_group_stride(int sx_ct, const uint32_t (&v)[32], float bias, const TcConvParams &p,
-                                                 long long xo, long long ao, long long sx, long long sa) {
-    switch (sx_ct) {
-        case 32: epi_group_fast<FMT, 32, MODE>(v, bias, p, xo, ao, sx, sa); return;
-        case 64: epi_group_fast<FMT, 64, MODE>(v, bias, p, xo, ao, sx, sa); return;
-        case 128: epi_group_fast<FMT, 128, MODE>(v, bias, p, xo, ao, sx, sa); return;
-        case 256: epi_group_fast<FMT, 256, MODE>(v, bias, p, xo, ao, sx, sa); return;
-        default: epi_group_fast<FMT, 0, MODE>(v, bias, p, xo, ao, sx, sa); return;
+__device__ __forceinline__ void epi_group16_c(int c_ct, const uint32_t (&v)[16], float bias, const TcConvParams &p,
+                                              const EpiLoads &res, float *px, uint16_t *pa) {
+    switch (c_ct) {
+        case 32: epi_group16<FMT, 32, MODE>(v, bias, p, res, px, pa); return;
+        case 64: epi_group16<FMT, 64, MODE>(v, bias, p, res, px, pa); return;
+        case 128: epi_group16<FMT, 128, MODE>(v, bias, p, res, px, pa); return;
+        case 256: epi_group16<FMT, 256, MODE>(v, bias, p, res, px, pa); return;
+        default: epi_group16<FMT, 0, MODE>(v, bias, p, res, px, pa); return;
     }
 }
-
 template <int FMT>
-__device__ __forceinline__ void epi_group_dispatch(int mode, int sx_ct, const uint32_t (&v)[32], float bias,
-                                                   const TcConvParams &p, long long xo, long long ao, long long sx,
-                                                   long long sa) {
+__device__ __forceinline__ void epi_group16_dispatch(int mode, int c_ct, const uint32_t (&v)[16], float bias,
+                                                     const TcConvParams &p, const EpiLoads &res, float *px, uint16_t *pa) {
     switch (mode) {
-        case EPI_A: epi_group_stride<FMT, EPI_A>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
-        case EPI_RXA: epi_group_stride<FMT, EPI_RXA>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
-        case EPI_RX: epi_group_stride<FMT, EPI_RX>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
-        case EPI_RCX: epi_group_stride<FMT, EPI_RCX>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
-        case EPI_RCDXA: epi_group_stride<FMT, EPI_RCDXA>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
-        case EPI_RCDX: epi_group_stride<FMT, EPI_RCDX>(sx_ct, v, bias, p, xo, ao, sx, sa); return;
-        case EPI_XA:   // upsample: pitches s*cout are 64 / 128 / 1024 / 2048 for V1
-            switch (sx_ct) {
-                case 64: epi_group_fast<FMT, 64, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
-                case 128: epi_group_fast<FMT, 128, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
-                case 1024: epi_group_fast<FMT, 1024, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
-                case 2048: epi_group_fast<FMT, 2048, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
-                default: epi_group_fast<FMT, 0, EPI_XA>(v, bias, p, xo, ao, sx, sa); return;
-            }
-        default: epi_group_fast<FMT, 0, EPI_GENERIC>(v, bias, p, xo, ao, sx, sa); return;
+        case EPI_A: epi_group16_c<FMT, EPI_A>(c_ct, v, bias, p, res, px, pa); return;
+        case EPI_RXA: epi_group16_c<FMT, EPI_RXA>(c_ct, v, bias, p, res, px, pa); return;
+        case EPI_RX: epi_group16_c<FMT, EPI_RX>(c_ct, v, bias, p, res, px, pa); return;
+        case EPI_RCX: epi_group16_c<FMT, EPI_RCX>(c_ct, v, bias, p, res, px, pa); return;
+        case EPI_RCDXA: epi_group16_c<FMT, EPI_RCDXA>(c_ct, v, bias, p, res, px, pa); return;
+        default: epi_group16_c<FMT, EPI_RCDX>(c_ct, v, bias, p, res, px, pa); return;
     }
 }
 
@@ -370,11 +356,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ===== epilogue warps: thread = output row (channel), registers = time positions =====
         const int ew = warp - PRODUCER_WARPS;
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
-        constexpr int SHARERS = EPI_WARPS / 4;              // warps sharing a quarter split the columns
-        constexpr int COLS_PER = TN / SHARERS;
-        const int col_lo = (ew / 4) * COLS_PER;
-        const long long sx = (long long)p.out_stride * p.cout;      // fp32 elements between time positions
-        const long long sa = (long long)p.out_stride * p.out_a_ld;  // 16-bit elements between time positions
+        constexpr int SHARERS = EPI_WARPS / 4;              // warps sharing a lane quarter split the columns
+        // narrow layers replicate their weight rows `rep` times over the 128 lanes; replica r is read by
+        // the warps of its lane quarters and covers columns [r*TN/rep, (r+1)*TN/rep)
+        const int qpc = 4 / p.rep;                          // lane quarters per replica
+        const int cols_per_warp = TN / p.rep / SHARERS;     // 64 / 32 / 16
+        const int col_lo = (quarter / qpc) * (TN / p.rep) + (ew / 4) * cols_per_warp;
+        const int r_in_copy = (quarter % qpc) * 32 + lane;  // output row of this thread within the m-block
         // kernel-uniform epilogue specialisation
         const bool R = p.res != nullptr, C = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
                    A = p.out_a != nullptr;
@@ -383,26 +371,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                        : (R && !C && !D && X && !A) ? EPI_RX
                        : (R && C && !D && X && !A) ? EPI_RCX
                        : (R && C && D && X && A) ? EPI_RCDXA
-                       : (R && C && D && X && !A) ? EPI_RCDX
-                       : (!R && !C && !D && X && A) ? EPI_XA : EPI_GENERIC;
-        const int sx_ct = (!A || p.out_a_ld == p.cout) ? (int)sx : 0;
-        // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one
-        // tile ahead and spread over all epilogue threads: turns the per-group HBM round trips of
-        // the (few) active warps into L2 hits.  Only for unit-stride layers (upsamples read neither).
+                       : (R && C && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
+        const bool unit = p.out_stride == 1 && p.out_off0 == 0 && p.n_total == p.cout && mode != EPI_GENERIC;
+        const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
+        // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one tile ahead,
+        // spread over all epilogue threads
         const int et = threadIdx.x - PRODUCER_WARPS * 32;          // 0 .. EPI_WARPS*32-1
         auto prefetch_tile = [&](int tile) {
-            if (!(R || C) || p.out_stride != 1) return;
+            if (!(R || C) || !unit) return;
             const int n0p = (tile % p.m_blocks) * TM;
             const int restp = tile / p.m_blocks;
             const int i0p = (restp % p.t_tiles) * TN, bp = restp / p.t_tiles;
             const int rows_ch = (p.n_total - n0p) < TM ? (p.n_total - n0p) : TM;   // channels of this m-block
-            const int lines_per_row = (rows_ch * 4 + 127) / 128;
-            const int n_lines = TN * lines_per_row;
+            const int lines_per_row = (rows_ch * 16 + 127) / 128;                  // one t/4 row = rows_ch * 16 bytes
+            const int n_lines = (TN / 4) * lines_per_row;
             for (int l = et; l < n_lines; l += EPI_WARPS * 32) {
-                const int row = l / lines_per_row, seg = l - row * lines_per_row;
-                const int t = i0p + row;
-                if (t < p.n_pos && t < p.L_out) {
-                    const long long off = ((long long)bp * p.L_out + t) * p.cout + n0p + seg * 32;
+                const int row4 = l / lines_per_row, seg = l - row4 * lines_per_row;
+                const int t = i0p + row4 * 4;
+                if (t < p.n_pos) {
+                    const long long off = (((long long)bp * p.L4 + (t >> 2)) * p.cout + n0p) * 4 + seg * 32;
                     if (R) prefetch_l2(p.res + off);
                     if (C) prefetch_l2(p.out_x + off);
                 }
@@ -417,8 +404,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int rest = tile / p.m_blocks;
             const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
             const uint32_t buf = tl % ACC_STAGES;
-            const int nq = n0 + quarter * 32;               // first output row of this warp
-            const int n = nq + lane;                        // global output row of this thread
+            const int nq = n0 + (quarter % qpc) * 32;       // first output row of this warp
+            const int n = n0 + r_in_copy;                   // global output row of this thread
             const bool row_ok = n < p.n_total;
             const int phase = nq / p.cout;                  // warp-uniform (cout is a multiple of 32)
             const int co = n - phase * p.cout;
@@ -427,28 +414,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
             const bool quarter_used = nq < p.n_total;       // warp-uniform
             const bool rows_full = nq + 32 <= p.n_total;    // warp-uniform
+            const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
+            // fully valid unit-stride group: 128-bit fast path
+            auto group_fast = [&](int ibase) { return unit && rows_full && ibase + 16 <= n_valid; };
+            auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + co) * 4; };
+            // issue the first group's residual loads before waiting for the accumulator
+            EpiLoads cur{}, nxt{};
+            if (quarter_used && R && group_fast(i0 + col_lo)) epi_load16<0>(nxt, res_ptr(i0 + col_lo), p.cout);
             if (ew == 1 && lane == 0) VTTS_TRACE(8);
             mbar_wait_relaxed(&acc_full[buf], (tl / ACC_STAGES) & 1u);
             if (ew == 1 && lane == 0) VTTS_TRACE(9);
             tc_fence_after();
             if (quarter_used) {
-                for (int cg = 0; cg < COLS_PER; cg += 32) {
+                for (int cg = 0; cg < cols_per_warp; cg += 16) {
                     const int col = col_lo + cg;
                     const int ibase = i0 + col;
                     if (ibase >= p.n_pos) break;            // warp-uniform: nothing valid beyond
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN + (uint32_t)col, v);
+                    uint32_t v[16];
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN + (uint32_t)col, v);
+                    cur = nxt;
+                    const bool fast = group_fast(ibase);
+                    if (R && cg + 16 < cols_per_warp && group_fast(ibase + 16)) epi_load16<0>(nxt, res_ptr(ibase + 16), p.cout);
                     tmem_ld_wait();
-                    const long long t_first = (long long)ibase * p.out_stride + p.out_off0 + phase;
-                    const long long t_last = t_first + 31LL * p.out_stride;
-                    const long long row0 = (long long)b * p.L_out + t_first;   // output row of element 0
-                    const long long xo = row0 * p.cout + co;
-                    const long long ao = row0 * p.out_a_ld + co;
-                    const bool full = rows_full && (ibase + 32 <= p.n_pos) && t_first >= 0 && t_last < p.L_out;
-                    if (full) {
-                        epi_group_dispatch<FMT>(mode, sx_ct, v, bias, p, xo, ao, sx, sa);
+                    if (fast) {
+                        float *px = X ? p.out_x + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + co) * 4 : nullptr;
+                        uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + ibase) * p.out_a_ld + co : nullptr;
+                        epi_group16_dispatch<FMT>(mode, c_ct, v, bias, p, cur, px, pa);
                     } else {
-                        epi_group_edge<FMT>(v, bias, p, row_ok, ibase, t_first, xo, ao, sx, sa);
+                        epi_group16_edge<FMT>(v, bias, p, row_ok, b, ibase, phase, co);
                     }
                 }
             }
@@ -531,9 +524,13 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     if (rowb == 64) { p.act_stages = 6; p.w_stages = 8; }
     else if (p.chunks == 1) { p.act_stages = 4; p.w_stages = 4; }
     else { p.act_stages = 2; p.w_stages = 8; }
-    p.w_rows = p.n_total >= TM ? TM : ((p.n_total + 31) / 32) * 32;
+    // narrow layers (32 / 64 output rows): the packed weights repeat the rows 4x / 2x over the 128 lanes so
+    // that every TMEM lane quarter (= every SM sub-partition's epilogue warps) holds a replica
+    p.rep = (p.m_blocks == 1 && (p.n_total == 32 || p.n_total == 64)) ? TM / p.n_total : 1;
+    p.w_rows = (p.rep > 1 || p.n_total >= TM) ? TM : ((p.n_total + 31) / 32) * 32;
     // quarters that hold real rows in every tile (a partial last m-block keeps all warps in the handshake)
-    p.epi_quarters = (p.m_blocks == 1 && p.n_total < TM) ? (p.n_total + 31) / 32 : 4;
+    p.epi_quarters = (p.rep == 1 && p.m_blocks == 1 && p.n_total < TM) ? (p.n_total + 31) / 32 : 4;
+    p.L4 = (p.L_out + 3) / 4;
     L.p = p;
     L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc: %zu B shared memory", L.smem);
@@ -562,12 +559,14 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
 // Conv1d (cout,cin,k): n = co, tap j = kernel index.
 // ConvTranspose1d (cin,cout,k), stride s: n = q*cout + co, tap j reads x[i0 - j], weight index q + j*s.
 __global__ void pack_tc_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int fmt, int kind, int cin,
-                               int cout, int k, int s, int taps, int n_pad, int ci_pad) {
+                               int cout, int k, int s, int taps, int n_pad, int ci_pad, int n_rows_real) {
     const size_t total = (size_t)taps * n_pad * ci_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int ci = (int)(idx % ci_pad);
         const size_t rest = idx / ci_pad;
-        const int n = (int)(rest % n_pad), j = (int)(rest / n_pad);
+        int n = (int)(rest % n_pad);
+        const int j = (int)(rest / n_pad);
+        if (n_rows_real == 32 || n_rows_real == 64) n %= n_rows_real;   // replicate narrow layers over all 128 lanes
         float v = 0.f;
         if (ci < cin) {
             if (kind == 0) {
@@ -581,34 +580,62 @@ __global__ void pack_tc_kernel(const float *__restrict__ w, uint16_t *__restrict
     }
 }
 
-// conv_post on channels-last fp32 input: y[b, 0, t] = tanh(bias + sum_k sum_ci w[ci,k] * lrelu(x[b, t+k-h, ci]))
-// (generator.py:108-120; kept in fp32 -- SURVEY.md section 0: output_conv dominates the bf16 error).
-// HBM-bound: reads C*4 bytes per sample once (neighbouring taps hit L1), writes 4.
+// conv_post on the time-packed fp32 stream ([b][t/4][c][4], see the epilogue helpers):
+// y[b, oc, t] = tanh(bias + sum_k sum_ci w[k][ci] * lrelu(x[b, t+k-h, ci]))
+// (generator.py:108-120; kept in fp32 -- the output conv dominates the 16-bit error).
+// HBM-bound: reads C*4 bytes per sample once (neighbouring taps come from shared memory), writes 4.
 template <int C>
 __global__ void __launch_bounds__(256)
-conv_post_cl_kernel(const float *__restrict__ x, const float *__restrict__ w /* [k][C] */, const float *__restrict__ bias,
-                    float *__restrict__ y, int L, int ksize, float slope, int out_channels, int oc) {
-    extern __shared__ float s_tile[];  // [(256 + ksize - 1)][C + 1]
-    const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;
-    const int rows = 256 + ksize - 1;
-    const float *xb = x + (size_t)b * L * C;
-    for (int idx = threadIdx.x; idx < rows * C; idx += 256) {
-        const int r = idx / C, c = idx - r * C;
-        const int t = t0 - h + r;
-        s_tile[r * (C + 1) + c] = (t >= 0 && t < L) ? lrelu(__ldg(xb + (size_t)t * C + c), slope) : 0.f;
+conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /* [k][C] */, const float *__restrict__ bias,
+                     float *__restrict__ y, int L, int L4, int ksize, float slope, int out_channels, int oc) {
+    extern __shared__ float s_tile[];  // [(256 + 8)][C + 1] rows = time t0-4 .. t0+259
+    const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;   // h <= 4
+    constexpr int ROWS = 256 + 8;
+    const float *xb = x + (size_t)b * L4 * C * 4;
+    // memory order: (t/4, c, t%4); tile covers t in [t0-4, t0+260)
+    for (int m = threadIdx.x; m < ROWS * C; m += 256) {
+        const int dt = m & 3, c = (m >> 2) % C, r4 = (m >> 2) / C;
+        const int t = t0 - 4 + r4 * 4 + dt;
+        float v = 0.f;
+        if (t >= 0 && t < L) v = lrelu(__ldg(xb + ((size_t)(t >> 2) * C + c) * 4 + dt), slope);
+        s_tile[(r4 * 4 + dt) * (C + 1) + c] = v;
     }
     __syncthreads();
     const int t = t0 + threadIdx.x;
     if (t >= L) return;
     float acc = 0.f;
     for (int k = 0; k < ksize; ++k) {
-        const float *row = s_tile + (threadIdx.x + k) * (C + 1);
+        const float *row = s_tile + (threadIdx.x + 4 - h + k) * (C + 1);
         const float *wk = w + k * C;
 #pragma unroll 8
         for (int c = 0; c < C; ++c) acc = fmaf(__ldg(wk + c), row[c], acc);
     }
     if (bias) acc += __ldg(bias + oc);
     y[((size_t)b * out_channels + oc) * L + t] = tanhf(acc);
+}
+
+// debug / test layout converters for the time-packed fp32 stream
+__global__ void tp4_to_cf_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L, int L4) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < L) y[((size_t)b * C + c) * L + t] = x[(((size_t)b * L4 + (t >> 2)) * C + c) * 4 + (t & 3)];
+}
+__global__ void cf_to_tp4_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int L, int L4) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < L) y[(((size_t)b * L4 + (t >> 2)) * C + c) * 4 + (t & 3)] = x[((size_t)b * C + c) * L + t];
+}
+static int launch_tp4_to_cf(const float *x, float *y, int B, int C, int L, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(L, 256), (unsigned)C, (unsigned)B);
+    tp4_to_cf_kernel<<<grid, 256, 0, st>>>(x, y, C, L, (L + 3) / 4);
+    VTTS_CHECK_LAUNCH();
+    return VTTS_OK;
+}
+static int launch_cf_to_tp4(const float *x, float *y, int B, int C, int L, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(L, 256), (unsigned)C, (unsigned)B);
+    cf_to_tp4_kernel<<<grid, 256, 0, st>>>(x, y, C, L, (L + 3) / 4);
+    VTTS_CHECK_LAUNCH();
+    return VTTS_OK;
 }
 
 }  // namespace tc
@@ -644,7 +671,7 @@ int tc_pack_layer(VttsGen *h, int layer, cudaStream_t st) {
     if (blocks > 8192) blocks = 8192;
     for (int fmt = 0; fmt < 2; ++fmt) {
         if (!l.w16[fmt]) VTTS_CHECK_CUDA(cudaMalloc(&l.w16[fmt], n * sizeof(uint16_t)));
-        pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w16[fmt], fmt, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad);
+        pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w16[fmt], fmt, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad, l.n_total);
         VTTS_CHECK_LAUNCH();
     }
     if (layer == h->idx_post) {
@@ -674,6 +701,7 @@ int tc_supported(const VttsGen *h, char *why, size_t why_len) {
             if ((c.resblock_kernel_sizes[j] - 1) * c.resblock_dilations[j][m] > HALO_MAX)
                 return fail("bf16 path needs (kernel-1)*dilation <= 64");
     if (c.kernel_size - 1 > HALO_MAX) return fail("input conv too wide");
+    if (c.kernel_size > 9) return fail("16-bit path: output conv kernel size must be <= 9");
     const int cl = c.channels >> c.num_upsamples;
     if (cl != 32 && cl != 64 && cl != 128) return fail("bf16 path: last stage width must be 32/64/128 for the fp32 output conv");
     return 1;
@@ -688,13 +716,13 @@ static int convT_len(int L, int s, int k, int p, int op) { return (L - 1) * s - 
 static TcPlan tc_plan(const VttsGen *h, int T) {
     TcPlan p;
     int ch = h->cfg.channels, L = T;
-    p.max_rows_c = (size_t)ch * L;
+    p.max_rows_c = (size_t)ch * ((L + 3) / 4 * 4);
     for (int i = 0; i < h->cfg.num_upsamples; ++i) {
         const Layer &u = h->layers[h->idx_up[i]];
         L = convT_len(L, u.stride, u.info.ksize, u.padding, u.output_padding);
         ch /= 2;
         p.C.push_back(ch); p.L.push_back(L);
-        size_t e = (size_t)ch * (size_t)(L > 0 ? L : 0);
+        size_t e = (size_t)ch * (size_t)(L > 0 ? (L + 3) / 4 * 4 : 0);
         if (e > p.max_rows_c) p.max_rows_c = e;
     }
     return p;
@@ -809,7 +837,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
     auto dump_f32 = [&](int id, const float *src_cl, int C, int L) -> int {
         if (dump_stage != id || !dump_out) return VTTS_OK;
         h->launch_count++;
-        return launch_cl_to_cf_f32(src_cl, dump_out, B, C, L, st);
+        return launch_tp4_to_cf(src_cl, dump_out, B, C, L, st);
     };
 
     // global conditioning bias (tiny 1x1 conv, fp32 CUDA cores)
@@ -895,15 +923,16 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         const int C = post.info.cin, k = post.info.ksize;
         const float *wt = post.w_aux;  // [oc][k][ci], packed at load time
         dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
-        const size_t smem = (size_t)(256 + k - 1) * (C + 1) * sizeof(float);
+        if (k > 9) return set_error(VTTS_E_UNSUPPORTED, "conv_post: kernel size %d > 9", k);
+        const size_t smem = (size_t)(256 + 8) * (C + 1) * sizeof(float);
         for (int oc = 0; oc < post.info.cout; ++oc) {
             const float *w_oc = wt + (size_t)oc * k * C;
             const float *bias = post.has_bias ? post.bias : nullptr;
 #define VTTS_POST(CC)                                                                                         \
     do {                                                                                                      \
         if (smem > 48 * 1024)                                                                                 \
-            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_post_cl_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv_post_cl_kernel<CC><<<grid, 256, smem, st>>>(bf.x_cs, w_oc, bias, wav, L, k, cfg.final_lrelu_slope, post.info.cout, oc); \
+            VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tp4_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv_post_tp4_kernel<CC><<<grid, 256, smem, st>>>(bf.x_cs, w_oc, bias, wav, L, (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc); \
     } while (0)
             if (C == 32) VTTS_POST(32);
             else if (C == 64) VTTS_POST(64);
@@ -1050,16 +1079,16 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
     VTTS_CHECK_CUDA(cudaMalloc(&a, (size_t)B * L * ci_pad * 2));
     VTTS_CHECK_CUDA(cudaMalloc(&wp, (size_t)ksize * n_pad * ci_pad * 2));
     VTTS_CHECK_CUDA(cudaMalloc(&oa, (size_t)B * L * cout * 2));
-    VTTS_CHECK_CUDA(cudaMalloc(&ox, (size_t)B * L * cout * 4));
-    VTTS_CHECK_CUDA(cudaMalloc(&rcl, (size_t)B * L * cout * 4));
+    const size_t L4p = (size_t)(L + 3) / 4 * 4;
+    VTTS_CHECK_CUDA(cudaMalloc(&ox, (size_t)B * L4p * cout * 4));
+    VTTS_CHECK_CUDA(cudaMalloc(&rcl, (size_t)B * L4p * cout * 4));
     int rc = launch_cf_to_cl_16(x, a, B, cin, L, ci_pad, slope_in, fmt, st);
     if (!rc) {
         size_t n = (size_t)ksize * n_pad * ci_pad;
-        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, fmt, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad);
+        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, fmt, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad, cout);
     }
     if (!rc && res) {
-        // channels-first -> channels-last fp32: reuse cl_to_cf with swapped roles (C <-> L)
-        rc = launch_cl_to_cf_f32(res, rcl, B, L, cout, st);  // treats input as (B, "L"=cout, "C"=L)
+        rc = launch_cf_to_tp4(res, rcl, B, cout, L, st);
     }
     if (!rc) {
         TcConvParams p{};
@@ -1071,7 +1100,7 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
         rc = tc_prepare(Lc, fmt, a, B, L, ci_pad, wp, n_pad, p);
         if (!rc) rc = tc_launch(Lc, st);
     }
-    if (!rc) rc = launch_cl_to_cf_f32(ox, y, B, cout, L, st);
+    if (!rc) rc = launch_tp4_to_cf(ox, y, B, cout, L, st);
     if (!rc && y_act) rc = launch_cl_16_to_cf_f32(oa, y_act, B, cout, L, cout, fmt, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(a); cudaFree(wp); cudaFree(oa); cudaFree(ox); cudaFree(rcl);
