@@ -115,8 +115,10 @@ struct TcConvParams {
     int rep;                   // weight rows replicated `rep` times across the 128 lanes (narrow layers: 128 / n_total)
     int L4;                    // ceil(L_out / 4): fp32 streams are stored time-packed [b][t/4][c][4]
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
-    // tile schedule: tile -> (m block fastest, then time tile, then batch)
-    int m_blocks, t_tiles, total_tiles;
+    // tile schedule: work item -> (m block fastest, then time-tile group, then batch); a cluster of
+    // `cluster` CTAs takes one work item: same m block (weights multicast), consecutive time tiles
+    int m_blocks, t_tiles, total_tiles;   // total_tiles = work items
+    int cluster, groups_per_batch;
 };
 
 // ---- epilogue helpers -------------------------------------------------------------------------------
@@ -259,9 +261,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
     const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
 
+    // cluster geometry: CL CTAs share every weight tile (each loads 1/CL of its rows and multicasts)
+    const int CL = p.cluster;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    // work item -> (first output row, first time position, batch); time tiles past the end are dummies
+    // (i0 >= n_pos: loads are zero-filled, the epilogue skips them) that keep the barrier protocol uniform
+    auto decode = [&](int item, int &n0, int &i0, int &b) {
+        n0 = (item % p.m_blocks) * TM;
+        const int rest = item / p.m_blocks;
+        b = rest / p.groups_per_batch;
+        i0 = ((rest % p.groups_per_batch) * CL + crank) * TN;
+    };
+
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
-        for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], (uint32_t)CL); }
         for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], (uint32_t)(p.epi_quarters * (EPI_WARPS / 4)));  // one arrival per participating warp
@@ -275,6 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -282,9 +299,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
             uint32_t it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-                const int rest = tile / p.m_blocks;
-                const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
+            for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
+                int n0, i0, b;
+                decode(tile, n0, i0, b);
+                (void)n0;
                 for (int c = 0; c < p.chunks; ++c, ++it) {
                     const uint32_t s = it % ACT_STAGES, ph = (it / ACT_STAGES) & 1u;
                     if (c == 0) VTTS_TRACE(4);
@@ -302,7 +320,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (lane == 0) {
             tma_prefetch_desc(&tm_w);
             uint32_t it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            const int my_rows = p.w_rows / CL;                  // this CTA's share of every weight tile
+            for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const int n0 = (tile % p.m_blocks) * TM;
                 for (int c = 0; c < p.chunks; ++c)
                     for (int j = 0; j < p.taps; ++j, ++it) {
@@ -310,8 +329,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         if ((c | j) == 0) VTTS_TRACE(6);
                         mbar_wait(&w_empty[s], ph ^ 1u);
                         if ((c | j) == 0) VTTS_TRACE(7);
-                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB));
-                        tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
+                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB));   // own + peer shares
+                        if (CL > 1)
+                            tma_load_3d_mc(s_w + (size_t)s * W_BYTES + (size_t)crank * my_rows * ROWB, &tm_w, &w_full[s],
+                                           c * CH, n0 + crank * my_rows, j, cmask);
+                        else
+                            tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
                     }
             }
         }
@@ -320,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
             uint32_t ia = 0, iw = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
                 VTTS_TRACE(0);
                 mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
@@ -344,7 +367,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                             const uint64_t bdesc = make_smem_desc(act_base + row * ROWB + ks * 32, ROWB, 0);
                             umma_bf16(tmem_d, adesc, bdesc, idesc, (uint32_t)((c | j | ks) != 0));
                         }
-                        umma_commit(&w_empty[sw]);   // weight stage reusable once these MMAs retire
+                        // weight stage reusable (in every CTA of the cluster) once these MMAs retire
+                        if (CL > 1) umma_commit_mc(&w_empty[sw], cmask); else umma_commit(&w_empty[sw]);
                     }
                     umma_commit(&act_empty[sa]);     // activation stage reusable
                 }
@@ -379,9 +403,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const int et = threadIdx.x - PRODUCER_WARPS * 32;          // 0 .. EPI_WARPS*32-1
         auto prefetch_tile = [&](int tile) {
             if (!(R || C) || !unit) return;
-            const int n0p = (tile % p.m_blocks) * TM;
-            const int restp = tile / p.m_blocks;
-            const int i0p = (restp % p.t_tiles) * TN, bp = restp / p.t_tiles;
+            int n0p, i0p, bp;
+            decode(tile, n0p, i0p, bp);
             const int rows_ch = (p.n_total - n0p) < TM ? (p.n_total - n0p) : TM;   // channels of this m-block
             const int lines_per_row = (rows_ch * 16 + 127) / 128;                  // one t/4 row = rows_ch * 16 bytes
             const int n_lines = (TN / 4) * lines_per_row;
@@ -395,14 +418,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 }
             }
         };
-        if ((int)blockIdx.x < p.total_tiles) prefetch_tile(blockIdx.x);
+        if (cid < p.total_tiles) prefetch_tile(cid);
         uint32_t tl = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-            if (tile + (int)gridDim.x < p.total_tiles) prefetch_tile(tile + gridDim.x);
+        for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
+            if (tile + ncl < p.total_tiles) prefetch_tile(tile + ncl);
             if (quarter >= p.epi_quarters) continue;        // this warp's TMEM lanes never hold real rows: prefetch duty only
-            const int n0 = (tile % p.m_blocks) * TM;
-            const int rest = tile / p.m_blocks;
-            const int i0 = (rest % p.t_tiles) * TN, b = rest / p.t_tiles;
+            int n0, i0, b;
+            decode(tile, n0, i0, b);
             const uint32_t buf = tl % ACC_STAGES;
             const int nq = n0 + (quarter % qpc) * 32;       // first output row of this warp
             const int n = n0 + r_in_copy;                   // global output row of this thread
@@ -454,6 +476,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
     if (warp == 2) tmem_dealloc(tmem_base, ACC_STAGES * TN);
 }
 
@@ -468,6 +491,12 @@ struct TcLaunch {
 static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
     return (size_t)act_stages * ACT_ROWS * rowb + (size_t)w_stages * TM * rowb +
            (size_t)(2 * act_stages + 2 * w_stages + 2 * ACC_STAGES) * 8 + 16;
+}
+
+static bool tc_cluster_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VTTS_TC_CLUSTER"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
 }
 
 static int tc_num_sms() {
@@ -488,8 +517,19 @@ static int tc_launch_t(const TcLaunch &L, cudaStream_t st) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    conv_tc_kernel<ROWB, FMT><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w, L.p);
-    VTTS_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = L.grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = (unsigned)L.p.cluster;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    VTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<ROWB, FMT>, L.tm_act, L.tm_w, L.p));
     return VTTS_OK;
 }
 
@@ -516,7 +556,11 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     p.chunks = ci_pad / ch;
     p.m_blocks = n_pad / TM;
     p.t_tiles = ceil_div(p.n_pos, TN);
-    const long long total = (long long)p.m_blocks * p.t_tiles * B;
+    // 2-CTA clusters multicast the weight tiles (halves the L2 -> SMEM weight traffic that bounds the
+    // MMA-heavy layers); not worth it when a batch row has a single time tile
+    p.cluster = (p.t_tiles >= 2 && tc_cluster_enabled()) ? 2 : 1;
+    p.groups_per_batch = ceil_div(p.t_tiles, p.cluster);
+    const long long total = (long long)p.m_blocks * p.groups_per_batch * B;
     if (total > 0x7fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "tc: too many tiles");
     p.total_tiles = (int)total;
     // pipeline depths: narrow (HBM-bound) layers need many activation bytes in flight, wide
@@ -535,7 +579,8 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc: %zu B shared memory", L.smem);
     const int sms = tc_num_sms();
-    L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
+    const int max_clusters = sms / p.cluster;
+    L.grid = dim3((unsigned)((p.total_tiles < max_clusters ? p.total_tiles : max_clusters) * p.cluster));
     {
         uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)L_in, (uint64_t)B};
         uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)L_in};
@@ -546,7 +591,7 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     {
         uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)n_pad, (uint64_t)p.taps};
         uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)n_pad};
-        uint32_t box[3] = {(uint32_t)ch, (uint32_t)p.w_rows, 1};
+        uint32_t box[3] = {(uint32_t)ch, (uint32_t)(p.w_rows / p.cluster), 1};
         int rc = make_tmap_bf16(&L.tm_w, w, 3, dims, str, box, rowb);
         if (rc) return rc;
     }
