@@ -167,6 +167,8 @@ int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const 
 /* Debug: enable per-tile clock64() tracing in vtts_dbg_conv1d_tc (block 0) and/or read the trace
  * buffer (16 stamps per tile, first 64 tiles) back to host memory. */
 int vtts_dbg_trace(int enable, long long *host_out, int n);
+/* Debug: raw tcgen05.mma issue/completion cycles (host_out[0] = issue loop, [1] = until complete). */
+int vtts_dbg_umma_bench(int N, int rowb, int row_shift, int reps, int M, int two_acc, long long *host_out);
 
 #ifdef __cplusplus
 }

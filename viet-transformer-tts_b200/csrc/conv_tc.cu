@@ -1100,6 +1100,68 @@ extern "C" int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float 
     return VTTS_OK;
 }
 
+// Raw tcgen05.mma throughput: `reps` x KSTEPS MMAs (M=128, N, K=16) issued back to back by one thread on
+// resident operands; cycles from first issue to commit completion are written to out[0..1].
+template <int ROWB>
+__global__ void __launch_bounds__(128, 1)
+umma_bench_kernel(long long *out, int N, int row_shift, int reps, int a_rows, int two_acc) {
+    constexpr int KSTEPS = ROWB / 32;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_a = smem;                         // 128 rows
+    uint8_t *s_b = smem + 128 * ROWB;            // 320 rows
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_b + 320 * ROWB);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
+    for (int i = threadIdx.x; i < (128 + 320) * ROWB / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_16(a_rows, N, 1);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint32_t a_addr = smem_u32(s_a) + ks * 32;
+                const uint32_t b_addr = smem_u32(s_b) + ((r % 11) * row_shift) * ROWB + ks * 32;
+                umma_bf16(tmem + ((two_acc && (r & 1)) ? 256u : 0u), make_smem_desc(a_addr, ROWB, 0),
+                          make_smem_desc(b_addr, ROWB, 0), idesc, 1u);
+            }
+        }
+        const long long t1 = clock64();
+        umma_commit(bar);
+        mbar_wait(bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+extern "C" int vtts_dbg_umma_bench(int N, int rowb, int row_shift, int reps, int M, int two_acc, long long *host_out) {
+    long long *d = nullptr;
+    VTTS_CHECK_CUDA(cudaMalloc(&d, 16));
+    const size_t smem = (size_t)(128 + 320) * rowb + 64;
+    if (rowb == 128) {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(umma_bench_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        umma_bench_kernel<128><<<148, 128, smem>>>(d, N, row_shift, reps, M, two_acc);
+    } else {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(umma_bench_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        umma_bench_kernel<64><<<148, 128, smem>>>(d, N, row_shift, reps, M, two_acc);
+    }
+    VTTS_CHECK_LAUNCH();
+    VTTS_CHECK_CUDA(cudaDeviceSynchronize());
+    VTTS_CHECK_CUDA(cudaMemcpy(host_out, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return VTTS_OK;
+}
+
 static int g_trace_on = 0;
 extern "C" int vtts_dbg_trace(int enable, long long *host_out, int n) {
     g_trace_on = enable;
