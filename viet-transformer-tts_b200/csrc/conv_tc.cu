@@ -284,7 +284,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
         fence_barrier_init();
     }
-    if (warp == 2) {  // MMA warp owns the TMEM allocation (all 512 columns: 2 accumulators)
+    // Warp roles.  The three single-thread roles sit in the HIGHEST warp ids: the warp scheduler favours high
+    // warp ids, and these threads are the critical path (a starved MMA issuer idles the tensor pipe).
+    constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2;
+    if (warp == WARP_MMA) {  // MMA warp owns the TMEM allocation (all 512 columns: 2 accumulators)
         tmem_alloc(tmem_slot, ACC_STAGES * TN);
         tmem_relinquish();
     }
@@ -294,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == WARP_ACT) {
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
@@ -315,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == WARP_W) {
         // ===== weight producer: one 128-row tile per (chunk, tap) =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_w);
@@ -338,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == WARP_MMA) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
@@ -361,12 +364,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         tc_fence_after();
                         const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
                         const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
+                        // descriptors of K step ks differ only in the start-address field (+32 bytes = +2 units)
+                        const uint64_t adesc0 = make_smem_desc(w_base, ROWB, 0);
+                        const uint64_t bdesc0 = make_smem_desc(act_base + row * ROWB, ROWB, 0);
 #pragma unroll
-                        for (int ks = 0; ks < KSTEPS; ++ks) {
-                            const uint64_t adesc = make_smem_desc(w_base + ks * 32, ROWB, 0);
-                            const uint64_t bdesc = make_smem_desc(act_base + row * ROWB + ks * 32, ROWB, 0);
-                            umma_bf16(tmem_d, adesc, bdesc, idesc, (uint32_t)((c | j | ks) != 0));
-                        }
+                        for (int ks = 0; ks < KSTEPS; ++ks)
+                            umma_bf16(tmem_d, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), idesc,
+                                      (uint32_t)((c | j | ks) != 0));
                         // weight stage reusable (in every CTA of the cluster) once these MMAs retire
                         if (CL > 1) umma_commit_mc(&w_empty[sw], cmask); else umma_commit(&w_empty[sw]);
                     }
@@ -378,7 +382,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
     } else {
         // ===== epilogue warps: thread = output row (channel), registers = time positions =====
-        const int ew = warp - PRODUCER_WARPS;
+        const int ew = warp;                                // epilogue warps are warps 0 .. EPI_WARPS-1
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
         constexpr int SHARERS = EPI_WARPS / 4;              // warps sharing a lane quarter split the columns
         // narrow layers replicate their weight rows `rep` times over the 128 lanes; replica r is read by
@@ -400,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
         // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one tile ahead,
         // spread over all epilogue threads
-        const int et = threadIdx.x - PRODUCER_WARPS * 32;          // 0 .. EPI_WARPS*32-1
+        const int et = threadIdx.x;                                // 0 .. EPI_WARPS*32-1
         auto prefetch_tile = [&](int tile) {
             if (!(R || C) || !unit) return;
             int n0p, i0p, bp;
@@ -443,9 +447,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             // issue the first group's residual loads before waiting for the accumulator
             EpiLoads cur{}, nxt{};
             if (quarter_used && R && group_fast(i0 + col_lo)) epi_load16<0>(nxt, res_ptr(i0 + col_lo), p.cout);
-            if (ew == 1 && lane == 0) VTTS_TRACE(8);
+            if (ew == 0 && lane == 0) VTTS_TRACE(8);
             mbar_wait_relaxed(&acc_full[buf], (tl / ACC_STAGES) & 1u);
-            if (ew == 1 && lane == 0) VTTS_TRACE(9);
+            if (ew == 0 && lane == 0) VTTS_TRACE(9);
             tc_fence_after();
             if (quarter_used) {
                 for (int cg = 0; cg < cols_per_warp; cg += 16) {
@@ -467,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     }
                 }
             }
-            if (ew == 1 && lane == 0) VTTS_TRACE(10);
+            if (ew == 0 && lane == 0) VTTS_TRACE(10);
             // all of this warp's tcgen05.ld have completed (wait::ld above): release the accumulator
             tc_fence_before();
             __syncwarp();
@@ -477,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
-    if (warp == 2) tmem_dealloc(tmem_base, ACC_STAGES * TN);
+    if (warp == WARP_MMA) tmem_dealloc(tmem_base, ACC_STAGES * TN);
 }
 
 struct TcLaunch {
