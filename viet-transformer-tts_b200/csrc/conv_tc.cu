@@ -343,9 +343,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
     } else if (warp == WARP_MMA) {
         // ===== MMA issuer =====
+        // One thread issues every tcgen05.mma.  The MMA queue is shallow, so any latency between two
+        // issues (barrier probe ~100 cycles, fence, commit) idles the tensor pipe.  The probes are therefore
+        // software-pipelined: the barrier of step n+1 is tested (non-blocking) BEFORE the MMAs of step n are
+        // issued, so its result is ready for free when step n+1 starts.
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
+            const int my_tiles = cid < p.total_tiles ? (p.total_tiles - cid + ncl - 1) / ncl : 0;
+            const uint32_t steps_per_tile = (uint32_t)(p.chunks * p.taps);
+            const uint32_t total_steps = (uint32_t)my_tiles * steps_per_tile;
             uint32_t ia = 0, iw = 0, tl = 0;
+            bool w_ready = total_steps > 0 ? mbar_try_wait(&w_full[0], 0u) : false;
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
                 VTTS_TRACE(0);
@@ -360,8 +368,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     const uint32_t act_base = smem_u32(s_act + (size_t)sa * ACT_BYTES);
                     for (int j = 0; j < p.taps; ++j, ++iw) {
                         const uint32_t sw = iw % W_STAGES;
-                        mbar_wait(&w_full[sw], (iw / W_STAGES) & 1u);
+                        if (!w_ready) mbar_wait(&w_full[sw], (iw / W_STAGES) & 1u);
                         tc_fence_after();
+                        // probe the next step's weight barrier now; consumed at the top of the next step
+                        const uint32_t iw1 = iw + 1;
+                        bool w_ready_next = false;
+                        if (iw1 < total_steps) w_ready_next = mbar_try_wait(&w_full[iw1 % W_STAGES], (iw1 / W_STAGES) & 1u);
                         const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
                         const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
                         // descriptors of K step ks differ only in the start-address field (+32 bytes = +2 units)
@@ -373,6 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                                       (uint32_t)((c | j | ks) != 0));
                         // weight stage reusable (in every CTA of the cluster) once these MMAs retire
                         if (CL > 1) umma_commit_mc(&w_empty[sw], cmask); else umma_commit(&w_empty[sw]);
+                        w_ready = w_ready_next;
                     }
                     umma_commit(&act_empty[sa]);     // activation stage reusable
                 }
