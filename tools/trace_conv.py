@@ -23,16 +23,17 @@ def run(B, C, L, k, d, with_res):
     t0 = t[0, 0]
     print(f"--- C={C} L={L} k={k} d={d} res={with_res}  (cycles relative to first MMA-thread stamp)")
     print("tile | mma:start accE_ok actF_ok issued | act:wait go | w:wait go | epi:wait accF_ok done")
-    for i in list(range(0, 12)) + list(range(40, 46)):
+    for i in list(range(0, 10)):
         r = t[i] - t0
         print(f"{i:4d} | {r[0]:8d} {r[1]:8d} {r[2]:8d} {r[3]:8d} | {r[4]:8d} {r[5]:8d} | {r[6]:8d} {r[7]:8d} | {r[8]:8d} {r[9]:8d} {r[10]:8d}")
-    e = t[8:40]
-    print(f"epilogue detail: accF_ok->ld_issue {np.mean(e[:,11]-e[:,9]):.0f}  tmem_ld+wait {np.mean(e[:,12]-e[:,11]):.0f}  "
-          f"group0 math+stores {np.mean(e[:,13]-e[:,12]):.0f}  2nd tmem_ld+wait {np.mean(e[:,14]-e[:,13]):.0f}  group1 {np.mean(e[:,10]-e[:,14]):.0f}")
-    per = np.diff(t[8:40, 3]).mean()
-    print(f"steady-state cycles per tile (MMA issue done): {per:.0f};  epilogue busy {np.mean(t[8:40,10]-t[8:40,9]):.0f};  "
-          f"mma wait act {np.mean(t[8:40,2]-t[8:40,1]):.0f}; mma wait accE {np.mean(t[8:40,1]-t[8:40,0]):.0f}; issue {np.mean(t[8:40,3]-t[8:40,2]):.0f}")
+    e = t[4:16]
+    steps = k * max(1, C // 64)
+    print(f"MMA-thread per step ({steps} steps/tile): wait_w {np.mean(e[:,11])/steps:.0f}  fence+issue {np.mean(e[:,12])/steps:.0f}  commit {np.mean(e[:,13])/steps:.0f} cycles")
+    per = np.diff(t[4:16, 3]).mean()
+    print(f"steady-state cycles per tile (MMA issue done): {per:.0f};  epilogue busy {np.mean(t[4:16,10]-t[4:16,9]):.0f};  "
+          f"mma wait act {np.mean(t[4:16,2]-t[4:16,1]):.0f}; mma wait accE {np.mean(t[4:16,1]-t[4:16,0]):.0f}; issue {np.mean(t[4:16,3]-t[4:16,2]):.0f}")
 if __name__ == "__main__":
-    run(16, 32, 194304, 3, 1, False)
-    run(16, 32, 194304, 11, 1, True)
-    run(16, 128, 48576, 3, 1, True)
+    run(16, 32, 194304, 11, 1, False)
+    run(16, 64, 97152, 11, 1, False)
+    run(16, 128, 48576, 11, 1, True)
+    run(16, 256, 6072, 11, 1, False)

@@ -343,23 +343,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
     } else if (warp == WARP_MMA) {
         // ===== MMA issuer =====
-        // One thread issues every tcgen05.mma.  The MMA queue is shallow, so any latency between two
-        // issues (barrier probe ~100 cycles, fence, commit) idles the tensor pipe.  The probes are therefore
-        // software-pipelined: the barrier of step n+1 is tested (non-blocking) BEFORE the MMAs of step n are
-        // issued, so its result is ready for free when step n+1 starts.
+        // One thread issues every tcgen05.mma.  The MMA queue is shallow, so latency between two issues idles
+        // the tensor pipe; measured on B200 a barrier probe costs ~300 cycles of thread time even when the
+        // barrier completed long ago.  Each step therefore probes the NEXT stage's barrier first and issues the
+        // current MMAs while that probe is in flight (umma_step*, one asm block so the order is ours).
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
             const int my_tiles = cid < p.total_tiles ? (p.total_tiles - cid + ncl - 1) / ncl : 0;
-            const uint32_t steps_per_tile = (uint32_t)(p.chunks * p.taps);
-            const uint32_t total_steps = (uint32_t)my_tiles * steps_per_tile;
+            const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)(p.chunks * p.taps);
             uint32_t ia = 0, iw = 0, tl = 0;
-            bool w_ready = total_steps > 0 ? mbar_try_wait(&w_full[0], 0u) : false;
+            uint32_t w_ready = 0;
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
                 VTTS_TRACE(0);
                 mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
                 VTTS_TRACE(1);
-                tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * TN;
                 for (int c = 0; c < p.chunks; ++c, ++ia) {
                     const uint32_t sa = ia % ACT_STAGES;
@@ -370,22 +368,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         const uint32_t sw = iw % W_STAGES;
                         if (!w_ready) mbar_wait(&w_full[sw], (iw / W_STAGES) & 1u);
                         tc_fence_after();
-                        // probe the next step's weight barrier now; consumed at the top of the next step
-                        const uint32_t iw1 = iw + 1;
-                        bool w_ready_next = false;
-                        if (iw1 < total_steps) w_ready_next = mbar_try_wait(&w_full[iw1 % W_STAGES], (iw1 / W_STAGES) & 1u);
                         const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
                         const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
                         // descriptors of K step ks differ only in the start-address field (+32 bytes = +2 units)
                         const uint64_t adesc0 = make_smem_desc(w_base, ROWB, 0);
                         const uint64_t bdesc0 = make_smem_desc(act_base + row * ROWB, ROWB, 0);
+                        if (CL > 1) {
 #pragma unroll
-                        for (int ks = 0; ks < KSTEPS; ++ks)
-                            umma_bf16(tmem_d, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), idesc,
-                                      (uint32_t)((c | j | ks) != 0));
-                        // weight stage reusable (in every CTA of the cluster) once these MMAs retire
-                        if (CL > 1) umma_commit_mc(&w_empty[sw], cmask); else umma_commit(&w_empty[sw]);
-                        w_ready = w_ready_next;
+                            for (int ks = 0; ks < KSTEPS; ++ks)
+                                umma_bf16(tmem_d, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), idesc,
+                                          (uint32_t)((c | j | ks) != 0));
+                            umma_commit_mc(&w_empty[sw], cmask);   // stage reusable in every CTA of the cluster
+                            w_ready = 0;
+                        } else {
+                            // next step's weight barrier (or, on the very last step, this one again: already complete)
+                            const uint32_t iw1 = (iw + 1 < total_steps) ? iw + 1 : iw;
+                            uint64_t *next_full = &w_full[iw1 % W_STAGES];
+                            const uint32_t next_par = (iw1 / W_STAGES) & 1u;
+                            if (KSTEPS == 4)
+                                w_ready = umma_step4(tmem_d, adesc0, bdesc0, idesc, (uint32_t)((c | j) != 0), next_full,
+                                                     next_par, &w_empty[sw]);
+                            else
+                                w_ready = umma_step2(tmem_d, adesc0, bdesc0, idesc, (uint32_t)((c | j) != 0), next_full,
+                                                     next_par, &w_empty[sw]);
+                        }
                     }
                     umma_commit(&act_empty[sa]);     // activation stage reusable
                 }
@@ -512,7 +518,7 @@ static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
 
 static bool tc_cluster_enabled() {
     static int on = -1;
-    if (on < 0) { const char *e = getenv("VTTS_TC_CLUSTER"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (on < 0) { const char *e = getenv("VTTS_TC_CLUSTER"); on = (e && e[0] == '1') ? 1 : 0; }  // off by default: no measured benefit
     return on == 1;
 }
 

@@ -154,6 +154,56 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
                  ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+// One pipeline step fused into a single asm block so the instruction order is ours:
+//   1. non-blocking probe of the NEXT stage's full-barrier (its ~100-300 cycle latency then overlaps
+//      the MMA issue instead of idling the shallow MMA queue),
+//   2. the K-step MMAs of the CURRENT stage,
+//   3. tcgen05.commit -> this stage's empty-barrier,
+//   4. materialise the probe result (consumed at the top of the next step).
+__device__ __forceinline__ uint32_t umma_step4(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
+                                               uint32_t acc_first, uint64_t *next_full, uint32_t next_parity,
+                                               uint64_t *this_empty) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(smem_u32(next_full)), "r"(next_parity),
+          "r"(smem_u32(this_empty))
+        : "memory");
+    return ready;
+}
+__device__ __forceinline__ uint32_t umma_step2(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
+                                               uint32_t acc_first, uint64_t *next_full, uint32_t next_parity,
+                                               uint64_t *this_empty) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(smem_u32(next_full)), "r"(next_parity),
+          "r"(smem_u32(this_empty))
+        : "memory");
+    return ready;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
