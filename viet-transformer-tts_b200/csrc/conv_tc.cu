@@ -80,7 +80,8 @@ constexpr int HALO_MAX = 64;       // (k-1)*d <= 64
 constexpr int ACT_ROWS = TN + HALO_MAX;
 constexpr int BOX_ROWS = 64;       // activation TMA box height
 constexpr int ACC_STAGES = 2;      // TMEM accumulators
-constexpr int PRODUCER_WARPS = 3;  // activation producer, weight producer, MMA issuer
+constexpr int W_PRODUCERS = 4;     // weight-producer warps (each owns the stages == its index mod 4)
+constexpr int PRODUCER_WARPS = 2 + W_PRODUCERS;  // activation producer, weight producers, MMA issuer
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
 
 // debug trace (vtts_dbg_trace_*): 16 stamps per tile for the first TRACE_TILES tiles of block 0
@@ -286,7 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     }
     // Warp roles.  The three single-thread roles sit in the HIGHEST warp ids: the warp scheduler favours high
     // warp ids, and these threads are the critical path (a starved MMA issuer idles the tensor pipe).
-    constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2;
+    constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 1 + W_PRODUCERS;
     if (warp == WARP_MMA) {  // MMA warp owns the TMEM allocation (all 512 columns: 2 accumulators)
         tmem_alloc(tmem_slot, ACC_STAGES * TN);
         tmem_relinquish();
@@ -318,16 +319,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 }
             }
         }
-    } else if (warp == WARP_W) {
-        // ===== weight producer: one 128-row tile per (chunk, tap) =====
+    } else if (warp >= WARP_W && warp < WARP_W + W_PRODUCERS) {
+        // ===== weight producers: one 128-row tile per (chunk, tap) step.  A producer iteration (empty-barrier
+        // probe + expect_tx + TMA issue) has ~1 us of serial latency, far more than the MMA time of a step, so
+        // W_PRODUCERS warps run round-robin over the steps; W_STAGES is a multiple of W_PRODUCERS, so each warp
+        // owns a fixed subset of the stages and the barriers need no cross-warp coordination. =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_w);
-            uint32_t it = 0, tl = 0;
             const int my_rows = p.w_rows / CL;                  // this CTA's share of every weight tile
+            const uint32_t me = (uint32_t)(warp - WARP_W);
+            uint32_t it = 0, tl = 0;
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const int n0 = (tile % p.m_blocks) * TM;
                 for (int c = 0; c < p.chunks; ++c)
                     for (int j = 0; j < p.taps; ++j, ++it) {
+                        if (it % W_PRODUCERS != me) continue;
                         const uint32_t s = it % W_STAGES, ph = (it / W_STAGES) & 1u;
                         if ((c | j) == 0) VTTS_TRACE(6);
                         mbar_wait(&w_empty[s], ph ^ 1u);
