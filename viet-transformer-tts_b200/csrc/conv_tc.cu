@@ -80,7 +80,7 @@ constexpr int HALO_MAX = 64;       // (k-1)*d <= 64
 constexpr int ACT_ROWS = TN + HALO_MAX;
 constexpr int BOX_ROWS = 64;       // activation TMA box height
 constexpr int ACC_STAGES = 2;      // TMEM accumulators
-constexpr int W_PRODUCERS = 4;     // weight-producer warps (each owns the stages == its index mod 4)
+constexpr int W_PRODUCERS = 1;     // weight-producer warps (each owns the stages == its index mod 4)
 constexpr int PRODUCER_WARPS = 2 + W_PRODUCERS;  // activation producer, weight producers, MMA issuer
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
 
@@ -302,13 +302,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
-            uint32_t it = 0, tl = 0;
+            uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 int n0, i0, b;
                 decode(tile, n0, i0, b);
                 (void)n0;
-                for (int c = 0; c < p.chunks; ++c, ++it) {
-                    const uint32_t s = it % ACT_STAGES, ph = (it / ACT_STAGES) & 1u;
+                for (int c = 0; c < p.chunks; ++c) {
                     if (c == 0) VTTS_TRACE(4);
                     mbar_wait(&act_empty[s], ph ^ 1u);
                     if (c == 0) VTTS_TRACE(5);
@@ -316,6 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     for (int bx = 0; bx < nbox; ++bx)
                         tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act,
                                     &act_full[s], c * CH, i0 + min_off + bx * BOX_ROWS, b);
+                    if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -327,14 +327,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (lane == 0) {
             tma_prefetch_desc(&tm_w);
             const int my_rows = p.w_rows / CL;                  // this CTA's share of every weight tile
-            const uint32_t me = (uint32_t)(warp - WARP_W);
-            uint32_t it = 0, tl = 0;
+            uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const int n0 = (tile % p.m_blocks) * TM;
                 for (int c = 0; c < p.chunks; ++c)
-                    for (int j = 0; j < p.taps; ++j, ++it) {
-                        if (it % W_PRODUCERS != me) continue;
-                        const uint32_t s = it % W_STAGES, ph = (it / W_STAGES) & 1u;
+                    for (int j = 0; j < p.taps; ++j) {
                         if ((c | j) == 0) VTTS_TRACE(6);
                         mbar_wait(&w_empty[s], ph ^ 1u);
                         if ((c | j) == 0) VTTS_TRACE(7);
@@ -344,20 +341,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                                            c * CH, n0 + crank * my_rows, j, cmask);
                         else
                             tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
+                        if (++s == W_STAGES) { s = 0; ph ^= 1u; }
                     }
             }
         }
     } else if (warp == WARP_MMA) {
         // ===== MMA issuer =====
-        // One thread issues every tcgen05.mma.  The MMA queue is shallow, so latency between two issues idles
-        // the tensor pipe; measured on B200 a barrier probe costs ~300 cycles of thread time even when the
-        // barrier completed long ago.  Each step therefore probes the NEXT stage's barrier first and issues the
-        // current MMAs while that probe is in flight (umma_step*, one asm block so the order is ours).
+        // One thread issues every tcgen05.mma.  ncu showed this thread to be instruction-latency bound: the
+        // MMA queue is shallow, so every dependent scalar instruction between two issues idles the tensor pipe.
+        // The loop therefore keeps all state incrementally (no div/mod, descriptors advanced by adds), and each
+        // step probes the NEXT stage's barrier before issuing the current MMAs (umma_step*).
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
+            const uint32_t wfull0 = smem_u32(w_full), wempty0 = smem_u32(w_empty);
+            const uint64_t adesc_first = make_smem_desc(smem_u32(s_w), ROWB, 0);       // weight stage 0
+            const uint64_t bdesc_first = make_smem_desc(smem_u32(s_act), ROWB, 0);     // activation stage 0, row 0
+            constexpr uint64_t A_STAGE_STEP = (uint64_t)(W_BYTES >> 4), B_STAGE_STEP = (uint64_t)(ACT_BYTES >> 4);
+            const long long tap0 = (long long)(p.tap_off0 - min_off) * (ROWB >> 4);    // row of tap 0, in 16-byte units
+            const long long tap_step = (long long)p.tap_step * (ROWB >> 4);
             const int my_tiles = cid < p.total_tiles ? (p.total_tiles - cid + ncl - 1) / ncl : 0;
-            const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)(p.chunks * p.taps);
-            uint32_t ia = 0, iw = 0, tl = 0;
+            uint32_t steps_left = (uint32_t)my_tiles * (uint32_t)(p.chunks * p.taps);
+            uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;
+            uint64_t adesc = adesc_first, bstage = bdesc_first;
             uint32_t w_ready = 0;
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
@@ -365,41 +370,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
                 VTTS_TRACE(1);
                 const uint32_t tmem_d = tmem_base + buf * TN;
-                for (int c = 0; c < p.chunks; ++c, ++ia) {
-                    const uint32_t sa = ia % ACT_STAGES;
-                    mbar_wait(&act_full[sa], (ia / ACT_STAGES) & 1u);
+                uint32_t acc = 0;                                            // first MMA of the tile overwrites
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(&act_full[sa], aph);
                     if (c == 0) VTTS_TRACE(2);
-                    const uint32_t act_base = smem_u32(s_act + (size_t)sa * ACT_BYTES);
-                    for (int j = 0; j < p.taps; ++j, ++iw) {
-                        const uint32_t sw = iw % W_STAGES;
-                        if (!w_ready) mbar_wait(&w_full[sw], (iw / W_STAGES) & 1u);
+                    uint64_t bdesc = bstage + (uint64_t)tap0;
+                    for (int j = 0; j < p.taps; ++j) {
+                        if (!w_ready) mbar_wait_addr(wfull0 + sw * 8u, wph);
                         tc_fence_after();
-                        const uint32_t w_base = smem_u32(s_w + (size_t)sw * W_BYTES);
-                        const uint32_t row = (uint32_t)(p.tap_off0 + j * p.tap_step - min_off);
-                        // descriptors of K step ks differ only in the start-address field (+32 bytes = +2 units)
-                        const uint64_t adesc0 = make_smem_desc(w_base, ROWB, 0);
-                        const uint64_t bdesc0 = make_smem_desc(act_base + row * ROWB, ROWB, 0);
+                        // next weight stage (on the very last step: this one again, already complete)
+                        uint32_t sn = sw + 1, pn = wph;
+                        if (sn == W_STAGES) { sn = 0; pn ^= 1u; }
+                        --steps_left;
+                        if (steps_left == 0) { sn = sw; pn = wph; }
                         if (CL > 1) {
 #pragma unroll
                             for (int ks = 0; ks < KSTEPS; ++ks)
-                                umma_bf16(tmem_d, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), idesc,
-                                          (uint32_t)((c | j | ks) != 0));
+                                umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, acc | (uint32_t)ks);
                             umma_commit_mc(&w_empty[sw], cmask);   // stage reusable in every CTA of the cluster
                             w_ready = 0;
+                        } else if (KSTEPS == 4) {
+                            w_ready = umma_step4(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
                         } else {
-                            // next step's weight barrier (or, on the very last step, this one again: already complete)
-                            const uint32_t iw1 = (iw + 1 < total_steps) ? iw + 1 : iw;
-                            uint64_t *next_full = &w_full[iw1 % W_STAGES];
-                            const uint32_t next_par = (iw1 / W_STAGES) & 1u;
-                            if (KSTEPS == 4)
-                                w_ready = umma_step4(tmem_d, adesc0, bdesc0, idesc, (uint32_t)((c | j) != 0), next_full,
-                                                     next_par, &w_empty[sw]);
-                            else
-                                w_ready = umma_step2(tmem_d, adesc0, bdesc0, idesc, (uint32_t)((c | j) != 0), next_full,
-                                                     next_par, &w_empty[sw]);
+                            w_ready = umma_step2(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
                         }
+                        acc = 1;
+                        bdesc += (uint64_t)tap_step;
+                        adesc += A_STAGE_STEP;
+                        const bool wrapped = (steps_left != 0) && (sn == 0);
+                        sw = sn; wph = pn;
+                        if (wrapped) adesc = adesc_first;
                     }
                     umma_commit(&act_empty[sa]);     // activation stage reusable
+                    bstage += B_STAGE_STEP;
+                    if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; bstage = bdesc_first; }
                 }
                 VTTS_TRACE(3);
                 umma_commit(&acc_full[buf]);         // accumulator complete -> epilogue

@@ -29,6 +29,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    if (mbar_try_wait_addr(bar_addr, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_addr(bar_addr, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("vtts: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -161,8 +182,8 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
 //   3. tcgen05.commit -> this stage's empty-barrier,
 //   4. materialise the probe result (consumed at the top of the next step).
 __device__ __forceinline__ uint32_t umma_step4(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
-                                               uint32_t acc_first, uint64_t *next_full, uint32_t next_parity,
-                                               uint64_t *this_empty) {
+                                               uint32_t acc_first, uint32_t next_full_addr, uint32_t next_parity,
+                                               uint32_t this_empty_addr) {
     uint32_t ready;
     asm volatile(
         "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"
@@ -179,14 +200,14 @@ __device__ __forceinline__ uint32_t umma_step4(uint32_t tmem_d, uint64_t a0, uin
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
         "selp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(ready)
-        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(smem_u32(next_full)), "r"(next_parity),
-          "r"(smem_u32(this_empty))
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(next_full_addr), "r"(next_parity),
+          "r"(this_empty_addr)
         : "memory");
     return ready;
 }
 __device__ __forceinline__ uint32_t umma_step2(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
-                                               uint32_t acc_first, uint64_t *next_full, uint32_t next_parity,
-                                               uint64_t *this_empty) {
+                                               uint32_t acc_first, uint32_t next_full_addr, uint32_t next_parity,
+                                               uint32_t this_empty_addr) {
     uint32_t ready;
     asm volatile(
         "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b;\n\t"
@@ -199,8 +220,8 @@ __device__ __forceinline__ uint32_t umma_step2(uint32_t tmem_d, uint64_t a0, uin
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
         "selp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(ready)
-        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(smem_u32(next_full)), "r"(next_parity),
-          "r"(smem_u32(this_empty))
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(next_full_addr), "r"(next_parity),
+          "r"(this_empty_addr)
         : "memory");
     return ready;
 }
