@@ -351,7 +351,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // MMA queue is shallow, so every dependent scalar instruction between two issues idles the tensor pipe.
         // The loop therefore keeps all state incrementally (no div/mod, descriptors advanced by adds), and each
         // step probes the NEXT stage's barrier before issuing the current MMAs (umma_step*).
-        if (lane == 0) {
+        // (the whole warp runs this loop converged; elect.sync inside the step picks the issuing lane)
+        {
             constexpr uint32_t idesc = make_idesc_16(TM, TN, FMT);
             const uint32_t wfull0 = smem_u32(w_full), wempty0 = smem_u32(w_empty);
             const uint64_t adesc_first = make_smem_desc(smem_u32(s_w), ROWB, 0);       // weight stage 0
@@ -366,14 +367,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             uint32_t w_ready = 0;
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
                 const uint32_t buf = tl % ACC_STAGES;
-                VTTS_TRACE(0);
+                if (lane == 0) VTTS_TRACE(0);
                 mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
-                VTTS_TRACE(1);
+                if (lane == 0) VTTS_TRACE(1);
                 const uint32_t tmem_d = tmem_base + buf * TN;
                 uint32_t acc = 0;                                            // first MMA of the tile overwrites
                 for (int c = 0; c < p.chunks; ++c) {
                     mbar_wait(&act_full[sa], aph);
-                    if (c == 0) VTTS_TRACE(2);
+                    if (c == 0 && lane == 0) VTTS_TRACE(2);
                     uint64_t bdesc = bstage + (uint64_t)tap0;
                     for (int j = 0; j < p.taps; ++j) {
                         if (!w_ready) mbar_wait_addr(wfull0 + sw * 8u, wph);
@@ -384,15 +385,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         --steps_left;
                         if (steps_left == 0) { sn = sw; pn = wph; }
                         if (CL > 1) {
+                            if (lane == 0) {
 #pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ++ks)
-                                umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, acc | (uint32_t)ks);
-                            umma_commit_mc(&w_empty[sw], cmask);   // stage reusable in every CTA of the cluster
+                                for (int ks = 0; ks < KSTEPS; ++ks)
+                                    umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, acc | (uint32_t)ks);
+                                umma_commit_mc(&w_empty[sw], cmask);   // stage reusable in every CTA of the cluster
+                            }
+                            __syncwarp();
                             w_ready = 0;
                         } else if (KSTEPS == 4) {
-                            w_ready = umma_step4(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
+                            w_ready = umma_step4_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
                         } else {
-                            w_ready = umma_step2(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
+                            w_ready = umma_step2_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
                         }
                         acc = 1;
                         bdesc += (uint64_t)tap_step;
@@ -401,12 +405,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         sw = sn; wph = pn;
                         if (wrapped) adesc = adesc_first;
                     }
-                    umma_commit(&act_empty[sa]);     // activation stage reusable
+                    umma_commit_elect(&act_empty[sa]);     // activation stage reusable
                     bstage += B_STAGE_STEP;
                     if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; bstage = bdesc_first; }
                 }
-                VTTS_TRACE(3);
-                umma_commit(&acc_full[buf]);         // accumulator complete -> epilogue
+                if (lane == 0) VTTS_TRACE(3);
+                umma_commit_elect(&acc_full[buf]);         // accumulator complete -> epilogue
             }
         }
     } else {

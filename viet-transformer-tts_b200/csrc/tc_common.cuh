@@ -225,6 +225,63 @@ __device__ __forceinline__ uint32_t umma_step2(uint32_t tmem_d, uint64_t a0, uin
         : "memory");
     return ready;
 }
+// Whole-warp variant: every lane executes it converged with warp-uniform operands (so the compiler keeps the
+// descriptors in uniform registers, no per-MMA R2UR waterfall); elect.sync picks the lane that issues.
+__device__ __forceinline__ uint32_t umma_step4_warp(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
+                                                    uint32_t acc_first, uint32_t next_full_addr, uint32_t next_parity,
+                                                    uint32_t this_empty_addr) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, e;\n\t.reg .b64 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(next_full_addr), "r"(next_parity),
+          "r"(this_empty_addr)
+        : "memory");
+    return ready;
+}
+// Whole-warp variant: every lane executes it converged with warp-uniform operands (so the compiler keeps the
+// descriptors in uniform registers, no per-MMA R2UR waterfall); elect.sync picks the lane that issues.
+__device__ __forceinline__ uint32_t umma_step2_warp(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
+                                                    uint32_t acc_first, uint32_t next_full_addr, uint32_t next_parity,
+                                                    uint32_t this_empty_addr) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, e;\n\t.reg .b64 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(next_full_addr), "r"(next_parity),
+          "r"(this_empty_addr)
+        : "memory");
+    return ready;
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {   // whole converged warp; one lane commits
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
