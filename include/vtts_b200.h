@@ -139,6 +139,15 @@ int vtts_gen_forward(VttsGen *h, const float *c, const float *g, float *wav, int
                      void *workspace, size_t workspace_bytes, int precision, int dump_stage,
                      float *dump_out, vtts_stream_t stream);
 
+/* Extension (not in the reference): padding trim for batched synthesis.  mel_len (device, B x int64, or
+ * NULL to disable) gives each row's valid mel frames; until reset, the 16-bit path of vtts_gen_forward
+ * skips every tile that starts at or beyond (mel_len[b] + margin_frames) frames.  Samples of row b below
+ * mel_len[b] * upsample_factor are bit-identical to the untrimmed call provided margin_frames covers the
+ * generator's receptive field (14 frames for V1; 16 is the documented default); samples beyond
+ * (mel_len[b] + margin_frames) * upsample_factor are zero or undefined.  The pointer must stay valid
+ * until the forward has run. */
+int vtts_gen_set_valid_lengths(VttsGen *h, const int64_t *mel_len, int margin_frames);
+
 /* Number of kernel launches the last vtts_gen_forward on this handle issued. */
 int vtts_gen_last_launch_count(const VttsGen *h);
 

@@ -153,3 +153,41 @@ def test_bf16_unsupported_width_fails_loudly():
     m = m.to(DEV).eval()
     with torch.no_grad(), pytest.raises(_lib.VttsError, match="-5"):
         m(torch.randn(1, 8, 16, device=DEV))
+
+
+def test_padding_trim_leaves_valid_samples_bit_identical():
+    """forward_trimmed (extension) skips the padded tail; every valid sample must equal forward()."""
+    m, _ = v1_model("fp16")
+    g = torch.Generator().manual_seed(11)
+    B, T = 6, 90
+    c = torch.randn(B, 80, T, generator=g).to(DEV)
+    lengths = torch.tensor([90, 61, 33, 5, 74, 1])
+    with torch.no_grad():
+        full = m(c)
+        trimmed = m.forward_trimmed(c, lengths.to(DEV))
+        again = m(c)  # the sticky length state must be cleared after the call
+    assert torch.equal(full, again)
+    up = m.upsample_factor
+    for b in range(B):
+        n = int(lengths[b]) * up
+        assert torch.equal(trimmed[b, :, :n], full[b, :, :n]), b
+        far = (int(lengths[b]) + m.TRIM_MARGIN_FRAMES) * up
+        far = (far + 255) // 256 * 256
+        if far < T * up:
+            assert torch.all(trimmed[b, :, far:] == 0), b
+
+
+def test_synthesizer_trim_matches_untrimmed_on_valid_audio():
+    m, _ = v1_model("fp16")
+    g = torch.Generator().manual_seed(12)
+    hs = torch.randn(4, 20, 96, generator=g)
+    ds = torch.randint(1, 6, (4, 20), generator=g)
+    ds[1, 9:] = 0
+    ds[3, 3:] = 0
+    a = vtts_b200.Synthesizer(m, trim_padding=True)(hs.pin_memory(), ds.pin_memory())
+    wav_t, len_t = a[0].clone(), a[1].clone()
+    wav_f, len_f = vtts_b200.Synthesizer(m, trim_padding=False)(hs.pin_memory(), ds.pin_memory())
+    assert torch.equal(len_t, len_f)
+    for b in range(4):
+        n = int(len_t[b])
+        assert torch.equal(wav_t[b, :, :n], wav_f[b, :, :n])

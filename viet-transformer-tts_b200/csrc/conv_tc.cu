@@ -116,6 +116,10 @@ struct TcConvParams {
     int rep;                   // weight rows replicated `rep` times across the 128 lanes (narrow layers: 128 / n_total)
     int L4;                    // ceil(L_out / 4): fp32 streams are stored time-packed [b][t/4][c][4]
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
+    // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
+    // are skipped by every role (their outputs are never needed for the valid part of utterance b)
+    const long long *lens;
+    int len_margin, len_rate, len_extra;
     // tile schedule: work item -> (m block fastest, then time-tile group, then batch); a cluster of
     // `cluster` CTAs takes one work item: same m block (weights multicast), consecutive time tiles
     int m_blocks, t_tiles, total_tiles;   // total_tiles = work items
@@ -275,6 +279,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         b = rest / p.groups_per_batch;
         i0 = ((rest % p.groups_per_batch) * CL + crank) * TN;
     };
+    // padding trim (cluster launches keep every tile: both CTAs of a cluster must stay in lock step)
+    auto tile_live = [&](int i0, int b) -> bool {
+        if (p.lens == nullptr || CL > 1) return true;
+        const long long lim = (__ldg(p.lens + b) + p.len_margin) * (long long)p.len_rate + p.len_extra;
+        return (long long)i0 < lim;
+    };
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
@@ -307,6 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 int n0, i0, b;
                 decode(tile, n0, i0, b);
                 (void)n0;
+                if (!tile_live(i0, b)) continue;
                 for (int c = 0; c < p.chunks; ++c) {
                     if (c == 0) VTTS_TRACE(4);
                     mbar_wait(&act_empty[s], ph ^ 1u);
@@ -329,7 +340,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int my_rows = p.w_rows / CL;                  // this CTA's share of every weight tile
             uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
             for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
-                const int n0 = (tile % p.m_blocks) * TM;
+                int n0, i0w, bw;
+                decode(tile, n0, i0w, bw);
+                if (!tile_live(i0w, bw)) continue;
                 for (int c = 0; c < p.chunks; ++c)
                     for (int j = 0; j < p.taps; ++j) {
                         if ((c | j) == 0) VTTS_TRACE(6);
@@ -360,12 +373,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             constexpr uint64_t A_STAGE_STEP = (uint64_t)(W_BYTES >> 4), B_STAGE_STEP = (uint64_t)(ACT_BYTES >> 4);
             const long long tap0 = (long long)(p.tap_off0 - min_off) * (ROWB >> 4);    // row of tap 0, in 16-byte units
             const long long tap_step = (long long)p.tap_step * (ROWB >> 4);
-            const int my_tiles = cid < p.total_tiles ? (p.total_tiles - cid + ncl - 1) / ncl : 0;
-            uint32_t steps_left = (uint32_t)my_tiles * (uint32_t)(p.chunks * p.taps);
-            uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;
+            uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;   // tl counts PROCESSED tiles (accumulator ring)
             uint64_t adesc = adesc_first, bstage = bdesc_first;
             uint32_t w_ready = 0;
-            for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
+            for (int tile = cid; tile < p.total_tiles; tile += ncl) {
+                {
+                    int n0m, i0m, bm;
+                    decode(tile, n0m, i0m, bm);
+                    if (!tile_live(i0m, bm)) continue;
+                }
                 const uint32_t buf = tl % ACC_STAGES;
                 if (lane == 0) VTTS_TRACE(0);
                 mbar_wait(&acc_empty[buf], ((tl / ACC_STAGES) & 1u) ^ 1u);   // epilogue drained this accumulator
@@ -379,11 +395,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     for (int j = 0; j < p.taps; ++j) {
                         if (!w_ready) mbar_wait_addr(wfull0 + sw * 8u, wph);
                         tc_fence_after();
-                        // next weight stage (on the very last step: this one again, already complete)
+                        // next weight stage (after the very last step the probe simply reports "not ready")
                         uint32_t sn = sw + 1, pn = wph;
                         if (sn == W_STAGES) { sn = 0; pn ^= 1u; }
-                        --steps_left;
-                        if (steps_left == 0) { sn = sw; pn = wph; }
                         if (CL > 1) {
                             if (lane == 0) {
 #pragma unroll
@@ -401,9 +415,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         acc = 1;
                         bdesc += (uint64_t)tap_step;
                         adesc += A_STAGE_STEP;
-                        const bool wrapped = (steps_left != 0) && (sn == 0);
                         sw = sn; wph = pn;
-                        if (wrapped) adesc = adesc_first;
+                        if (sn == 0) adesc = adesc_first;
                     }
                     umma_commit_elect(&act_empty[sa]);     // activation stage reusable
                     bstage += B_STAGE_STEP;
@@ -411,6 +424,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 }
                 if (lane == 0) VTTS_TRACE(3);
                 umma_commit_elect(&acc_full[buf]);         // accumulator complete -> epilogue
+                ++tl;
             }
         }
     } else {
@@ -442,6 +456,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             if (!(R || C) || !unit) return;
             int n0p, i0p, bp;
             decode(tile, n0p, i0p, bp);
+            if (!tile_live(i0p, bp)) return;
             const int rows_ch = (p.n_total - n0p) < TM ? (p.n_total - n0p) : TM;   // channels of this m-block
             const int lines_per_row = (rows_ch * 16 + 127) / 128;                  // one t/4 row = rows_ch * 16 bytes
             const int n_lines = (TN / 4) * lines_per_row;
@@ -456,12 +471,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
         };
         if (cid < p.total_tiles) prefetch_tile(cid);
-        uint32_t tl = 0;
-        for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
+        uint32_t tl = 0;                                    // counts PROCESSED tiles (accumulator ring)
+        for (int tile = cid; tile < p.total_tiles; tile += ncl) {
             if (tile + ncl < p.total_tiles) prefetch_tile(tile + ncl);
             if (quarter >= p.epi_quarters) continue;        // this warp's TMEM lanes never hold real rows: prefetch duty only
             int n0, i0, b;
             decode(tile, n0, i0, b);
+            if (!tile_live(i0, b)) continue;
             const uint32_t buf = tl % ACC_STAGES;
             const int nq = n0 + (quarter % qpc) * 32;       // first output row of this warp
             const int n = n0 + r_in_copy;                   // global output row of this thread
@@ -509,6 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            ++tl;
         }
     }
     tc_fence_before();
@@ -669,9 +686,16 @@ __global__ void pack_tc_kernel(const float *__restrict__ w, uint16_t *__restrict
 template <int C>
 __global__ void __launch_bounds__(256)
 conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /* [k][C] */, const float *__restrict__ bias,
-                     float *__restrict__ y, int L, int L4, int ksize, float slope, int out_channels, int oc) {
+                     float *__restrict__ y, int L, int L4, int ksize, float slope, int out_channels, int oc,
+                     const long long *__restrict__ lens, int len_margin, int len_rate) {
     extern __shared__ float s_tile[];  // [(256 + 8)][C + 1] rows = time t0-4 .. t0+259
     const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;   // h <= 4
+    if (lens != nullptr && (long long)t0 >= (lens[b] + len_margin) * (long long)len_rate) {
+        // trimmed padding: defined (zero) output, no work
+        const int t = t0 + threadIdx.x;
+        if (t < L) y[((size_t)b * out_channels + oc) * L + t] = 0.f;
+        return;
+    }
     constexpr int ROWS = 256 + 8;
     const float *xb = x + (size_t)b * L4 * C * 4;
     // memory order: (t/4, c, t%4); tile covers t in [t0-4, t0+260)
@@ -876,7 +900,7 @@ static void prof_report() {
 }
 // one conv layer on the tensor cores
 static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, int B, int L_in, int L_out, TcConvParams p,
-                    cudaStream_t st) {
+                    cudaStream_t st, int in_rate = 0) {
     const bool transposed = l.info.kind == 1;
     const int s = transposed ? l.stride : 1;
     p.bias = l.has_bias ? l.bias : nullptr;
@@ -889,6 +913,13 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
     } else {
         p.taps = l.info.ksize; p.tap_off0 = -(l.info.ksize - 1) / 2 * l.info.dilation; p.tap_step = l.info.dilation;
         p.out_stride = 1; p.out_off0 = 0; p.n_pos = L_in;
+    }
+    // padding trim: positions of this GEMM run at `in_rate` positions per mel frame
+    if (h->trim_lens && in_rate > 0) {
+        p.lens = (const long long *)h->trim_lens;
+        p.len_margin = h->trim_margin;
+        p.len_rate = in_rate;
+        p.len_extra = transposed ? p.taps : 0;
     }
     TcLaunch L;
     int rc = tc_prepare(L, fmt, act, B, L_in, l.ci_pad, l.w16[fmt], pad_to(l.n_total, TM), p);
@@ -916,6 +947,15 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
     if (workspace_bytes < bf.total) return set_error(VTTS_E_WORKSPACE, "vtts_gen_forward: workspace %zu < %zu", workspace_bytes, bf.total);
     TcPlan plan = tc_plan(h, T);
     int rc;
+    // padding trim is only exact when every stage length is T * (product of scales)
+    int rate = 1;
+    {
+        int r = 1;
+        bool exact = true;
+        for (int i = 0; i < cfg.num_upsamples; ++i) { r *= cfg.upsample_scales[i]; exact = exact && plan.L[i] == T * r; }
+        if (!exact) h->trim_lens = nullptr;
+    }
+    const long long *trim_lens = (const long long *)h->trim_lens;
     auto dump_f32 = [&](int id, const float *src_cl, int C, int L) -> int {
         if (dump_stage != id || !dump_out) return VTTS_OK;
         h->launch_count++;
@@ -944,7 +984,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         p.bias_b = bias_b;
         p.out_a = bf.a_c; p.out_a_ld = cfg.channels; p.slope_out = cfg.lrelu_slope;
         p.out_x = (dump_stage == 0) ? bf.x_cs : nullptr;
-        if ((rc = run_conv(h, fmt, pre, bf.a_in, B, T, T, p, st))) return rc;
+        if ((rc = run_conv(h, fmt, pre, bf.a_in, B, T, T, p, st, rate))) return rc;
         if ((rc = dump_f32(0, bf.x_cs, cfg.channels, T))) return rc;
     }
     const uint16_t *cur_a = bf.a_c;
@@ -956,7 +996,8 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         {   // upsample: fp32 residual stream x_u + bf16 operand a_u = lrelu(x_u)
             TcConvParams p{};
             p.out_x = bf.x_u; p.out_a = bf.a_u; p.out_a_ld = C; p.slope_out = cfg.lrelu_slope;
-            if ((rc = run_conv(h, fmt, u, cur_a, B, L, Lo, p, st))) return rc;
+            if ((rc = run_conv(h, fmt, u, cur_a, B, L, Lo, p, st, rate))) return rc;
+            rate *= u.stride;
             if ((rc = dump_f32(2 * i + 1, bf.x_u, C, Lo))) return rc;
         }
         const bool last_stage = (i == cfg.num_upsamples - 1);
@@ -974,7 +1015,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                 if (cfg.use_additional_convs) {
                     TcConvParams p1{};  // xt = conv1(lrelu(x)); only its LeakyReLU'd bf16 copy is needed
                     p1.out_a = bf.a_t; p1.out_a_ld = C; p1.slope_out = cfg.lrelu_slope;
-                    if ((rc = run_conv(h, fmt, l1, ya, B, Lo, Lo, p1, st))) return rc;
+                    if ((rc = run_conv(h, fmt, l1, ya, B, Lo, Lo, p1, st, rate))) return rc;
                     fin = &h->layers[h->idx_c2[i][j][m]];
                     fin_in = bf.a_t;
                 }
@@ -992,7 +1033,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                 } else {
                     p2.out_a = na; p2.out_a_ld = C; p2.slope_out = cfg.lrelu_slope;
                 }
-                if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st))) return rc;
+                if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st, rate))) return rc;
                 yx = nx; ya = na;
             }
         }
@@ -1014,7 +1055,8 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
     do {                                                                                                      \
         if (smem > 48 * 1024)                                                                                 \
             VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tp4_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv_post_tp4_kernel<CC><<<grid, 256, smem, st>>>(bf.x_cs, w_oc, bias, wav, L, (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc); \
+        conv_post_tp4_kernel<CC><<<grid, 256, smem, st>>>(bf.x_cs, w_oc, bias, wav, L, (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc, \
+                                                          trim_lens, h->trim_margin, rate); \
     } while (0)
             if (C == 32) VTTS_POST(32);
             else if (C == 64) VTTS_POST(64);

@@ -312,6 +312,14 @@ extern "C" int vtts_gen_forward(VttsGen *h, const float *c, const float *g, floa
     return set_error(VTTS_E_INVALID, "vtts_gen_forward: unknown precision %d", precision);
 }
 
+extern "C" int vtts_gen_set_valid_lengths(VttsGen *h, const int64_t *mel_len, int margin_frames) {
+    VTTS_REQUIRE(h, "vtts_gen_set_valid_lengths: null handle");
+    VTTS_REQUIRE(margin_frames >= 0, "vtts_gen_set_valid_lengths: negative margin");
+    h->trim_lens = mel_len;
+    h->trim_margin = margin_frames;
+    return VTTS_OK;
+}
+
 extern "C" int vtts_gen_last_launch_count(const VttsGen *h) {
     VTTS_REQUIRE(h, "vtts_gen_last_launch_count: null handle");
     return h->launch_count;

@@ -39,6 +39,8 @@ struct VttsGen {
     int launch_count = 0;
     int device = 0;
     void *tc_state = nullptr;  // tensor-map cache etc. owned by conv_tc.cu
+    const int64_t *trim_lens = nullptr;  // device (B) valid mel frames for the NEXT forward (vtts_gen_set_valid_lengths)
+    int trim_margin = 0;
 };
 
 namespace vtts {

@@ -52,6 +52,7 @@ SIGNATURES = {
     "vtts_gen_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "vtts_gen_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vtts_gen_set_valid_lengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vtts_gen_last_launch_count": (C.c_int, [C.c_void_p]),
     "vtts_dbg_conv1d_fp32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),

@@ -175,7 +175,25 @@ class _GeneratorBase(nn.Module):
             return True
         return any(p.requires_grad for p in self.parameters())
 
-    def _run_kernels(self, c: torch.Tensor, g: Optional[torch.Tensor], dump_stage: int = -1):
+    TRIM_MARGIN_FRAMES = 16  # >= receptive field of the V1 generator in mel frames (about 14)
+
+    def forward_trimmed(self, c: torch.Tensor, lengths: torch.Tensor, g: Optional[torch.Tensor] = None,
+                        margin_frames: Optional[int] = None) -> torch.Tensor:
+        """Extension: like ``forward`` for a padded batch whose rows have ``lengths`` valid frames.
+
+        Work beyond ``lengths[b] + margin_frames`` frames is skipped; the first
+        ``lengths[b] * upsample_factor`` samples of row b are bit-identical to ``forward(c, g)``, later samples
+        are zero or undefined.  Synthesis only (no autograd).
+        """
+        if self.precision == "fp32":
+            return self._run_kernels(c, g)
+        lens = lengths.detach().to(c.device, torch.int64).contiguous()
+        if lens.numel() != c.shape[0]:
+            raise ValueError("lengths must have one entry per batch row")
+        m = self.TRIM_MARGIN_FRAMES if margin_frames is None else int(margin_frames)
+        return self._run_kernels(c, g, trim=(lens, m))
+
+    def _run_kernels(self, c: torch.Tensor, g: Optional[torch.Tensor], dump_stage: int = -1, trim=None):
         lib = _lib.load()
         if not c.is_cuda:
             raise RuntimeError(
@@ -216,8 +234,14 @@ class _GeneratorBase(nn.Module):
             if dump_stage >= 0:
                 ch, Ld = self._stage_shape(dump_stage, T)
                 dump = torch.empty((B, ch, Ld), dtype=torch.float32, device=dev)
-            _lib.check(lib.vtts_gen_forward(h, x.data_ptr(), _lib.ptr(gg), wav.data_ptr(), B, T, ws.data_ptr(),
-                                            ws.numel(), prec, dump_stage, _lib.ptr(dump), stream))
+            if trim is not None:
+                _lib.check(lib.vtts_gen_set_valid_lengths(h, trim[0].data_ptr(), trim[1]))
+            try:
+                _lib.check(lib.vtts_gen_forward(h, x.data_ptr(), _lib.ptr(gg), wav.data_ptr(), B, T, ws.data_ptr(),
+                                                ws.numel(), prec, dump_stage, _lib.ptr(dump), stream))
+            finally:
+                if trim is not None:
+                    lib.vtts_gen_set_valid_lengths(h, None, 0)
             self.last_launch_count = lib.vtts_gen_last_launch_count(h)
         if c.dtype != torch.float32:
             wav = wav.to(c.dtype)

@@ -27,13 +27,15 @@ def slice_decoder_stand_in(in_channels: int) -> Callable[[torch.Tensor], torch.T
 class Synthesizer:
     def __init__(self, generator, length_regulator: Optional[LengthRegulator] = None,
                  frames_to_mel: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, trim_padding: bool = True):
         self.generator = generator
         self.length_regulator = length_regulator or LengthRegulator()
         cfg = generator._gen_config()
         self.frames_to_mel = frames_to_mel or slice_decoder_stand_in(cfg.in_channels)
         self.device = torch.device(device) if device is not None else next(generator.parameters()).device
         self._pinned_out = None
+        # skip generator work on the padded tail of shorter utterances (valid samples are unaffected)
+        self.trim_padding = trim_padding
 
     @torch.no_grad()
     def __call__(self, hs: torch.Tensor, ds: torch.Tensor, alpha: float = 1.0, to_host: bool = True
@@ -43,7 +45,11 @@ class Synthesizer:
         hs_d = hs.to(dev, non_blocking=True)
         ds_d = ds.to(dev, non_blocking=True)
         frames, mel_len = self.length_regulator.forward_with_lengths(hs_d, ds_d, alpha)
-        wav = self.generator(self.frames_to_mel(frames))
+        mel = self.frames_to_mel(frames)
+        if self.trim_padding and hasattr(self.generator, "forward_trimmed"):
+            wav = self.generator.forward_trimmed(mel, mel_len)
+        else:
+            wav = self.generator(mel)
         wav_len = mel_len * self.generator.upsample_factor
         if not to_host:
             return wav, wav_len
