@@ -83,6 +83,7 @@ constexpr int ACC_STAGES = 2;      // TMEM accumulators
 constexpr int W_PRODUCERS = 1;     // weight-producer warps (each owns the stages == its index mod 4)
 constexpr int PRODUCER_WARPS = 2 + W_PRODUCERS;  // activation producer, weight producers, MMA issuer
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
+constexpr int MAX_TRIM_BATCH = 256; // padding trim keeps per-batch limits in shared memory
 
 // debug trace (vtts_dbg_trace_*): 16 stamps per tile for the first TRACE_TILES tiles of block 0
 constexpr int TRACE_TILES = 64;
@@ -111,6 +112,7 @@ struct TcConvParams {
     int chunks;             // K chunks (ci_pad / chunk channels)
     int taps, tap_off0, tap_step;
     int act_stages, w_stages;  // pipeline depths (shared memory is carved at run time)
+    int tps;                   // taps per pipeline step (2 for single-chunk layers: halves barrier ops per MMA)
     int w_rows;                // weight rows actually loaded per tile (<= 128; the rest of the A tile is don't-care)
     int epi_quarters;          // TMEM lane quarters holding real output rows in EVERY tile (1..4)
     int rep;                   // weight rows replicated `rep` times across the 128 lanes (narrow layers: 128 / n_total)
@@ -119,7 +121,7 @@ struct TcConvParams {
     // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
     // are skipped by every role (their outputs are never needed for the valid part of utterance b)
     const long long *lens;
-    int len_margin, len_rate, len_extra;
+    int len_margin, len_rate, len_extra, batch;
     // tile schedule: work item -> (m block fastest, then time-tile group, then batch); a cluster of
     // `cluster` CTAs takes one work item: same m block (weights multicast), consecutive time tiles
     int m_blocks, t_tiles, total_tiles;   // total_tiles = work items
@@ -254,11 +256,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     uint8_t *s_act = smem;
     const uint32_t ACT_STAGES = (uint32_t)p.act_stages, W_STAGES = (uint32_t)p.w_stages;
     uint8_t *s_w = smem + (size_t)ACT_STAGES * ACT_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + (size_t)W_STAGES * W_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + (size_t)W_STAGES * W_BYTES * p.tps);
     uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
     uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
     uint64_t *acc_full = w_empty + W_STAGES, *acc_empty = acc_full + ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
+    int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);   // [MAX_TRIM_BATCH] per-batch tile-start limits (padding trim)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
@@ -273,18 +276,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     // work item -> (first output row, first time position, batch); time tiles past the end are dummies
     // (i0 >= n_pos: loads are zero-filled, the epilogue skips them) that keep the barrier protocol uniform
-    auto decode = [&](int item, int &n0, int &i0, int &b) {
-        n0 = (item % p.m_blocks) * TM;
-        const int rest = item / p.m_blocks;
-        b = rest / p.groups_per_batch;
-        i0 = ((rest % p.groups_per_batch) * CL + crank) * TN;
+    // Work items are walked with a mixed-radix counter (m block, time group, batch) advanced by `ncl` with
+    // carries: no div/mod on the per-tile path of the single-thread roles.
+    struct TileIter {
+        int item, m, g, b, dm, dg, db, mb, gpb;
+        __device__ void init(int first, int step, int m_blocks, int groups) {
+            mb = m_blocks; gpb = groups;
+            item = first; m = first % mb; int r = first / mb; g = r % gpb; b = r / gpb;
+            dm = step % mb; r = step / mb; dg = r % gpb; db = r / gpb;
+        }
+        __device__ void next(int step) {
+            item += step;
+            m += dm; int c = 0;
+            if (m >= mb) { m -= mb; c = 1; }
+            g += dg + c; c = 0;
+            if (g >= gpb) { g -= gpb; c = 1; }
+            b += db + c;
+        }
     };
-    // padding trim (cluster launches keep every tile: both CTAs of a cluster must stay in lock step)
-    auto tile_live = [&](int i0, int b) -> bool {
-        if (p.lens == nullptr || CL > 1) return true;
-        const long long lim = (__ldg(p.lens + b) + p.len_margin) * (long long)p.len_rate + p.len_extra;
-        return (long long)i0 < lim;
+    auto decode = [&](const TileIter &it, int &n0, int &i0, int &b) {
+        n0 = it.m * TM;
+        b = it.b;
+        i0 = (it.g * CL + crank) * TN;
     };
+    // padding trim: per-batch position limits live in shared memory (filled below); cluster launches keep every
+    // tile because both CTAs of a cluster must stay in lock step
+    const bool trimming = p.lens != nullptr && CL == 1;
+    auto tile_live = [&](int i0, int b) -> bool { return !trimming || i0 < s_lim[b]; };
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
@@ -302,6 +320,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         tmem_alloc(tmem_slot, ACC_STAGES * TN);
         tmem_relinquish();
     }
+    if (p.lens != nullptr)
+        for (int i = threadIdx.x; i < p.batch; i += blockDim.x) {
+            const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate + p.len_extra;
+            s_lim[i] = lim > 0x7fffffffLL ? 0x7fffffff : (int)lim;
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -313,9 +336,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
             uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
-            for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
+            TileIter ti;
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch); ti.item < p.total_tiles; ti.next(ncl), ++tl) {
                 int n0, i0, b;
-                decode(tile, n0, i0, b);
+                decode(ti, n0, i0, b);
                 (void)n0;
                 if (!tile_live(i0, b)) continue;
                 for (int c = 0; c < p.chunks; ++c) {
@@ -339,21 +363,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             tma_prefetch_desc(&tm_w);
             const int my_rows = p.w_rows / CL;                  // this CTA's share of every weight tile
             uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
-            for (int tile = cid; tile < p.total_tiles; tile += ncl, ++tl) {
+            const int tps = p.tps;                               // taps per stage (the box depth of tm_w)
+            const size_t stage_bytes = (size_t)W_BYTES * tps;
+            TileIter ti;
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch); ti.item < p.total_tiles; ti.next(ncl), ++tl) {
                 int n0, i0w, bw;
-                decode(tile, n0, i0w, bw);
+                decode(ti, n0, i0w, bw);
                 if (!tile_live(i0w, bw)) continue;
                 for (int c = 0; c < p.chunks; ++c)
-                    for (int j = 0; j < p.taps; ++j) {
+                    for (int j = 0; j < p.taps; j += tps) {
                         if ((c | j) == 0) VTTS_TRACE(6);
                         mbar_wait(&w_empty[s], ph ^ 1u);
                         if ((c | j) == 0) VTTS_TRACE(7);
-                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB));   // own + peer shares
+                        // a box past the last tap is zero-filled by TMA: the padded tap contributes nothing
+                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));   // own + peer shares
                         if (CL > 1)
-                            tma_load_3d_mc(s_w + (size_t)s * W_BYTES + (size_t)crank * my_rows * ROWB, &tm_w, &w_full[s],
+                            tma_load_3d_mc(s_w + (size_t)s * stage_bytes + (size_t)crank * my_rows * ROWB, &tm_w, &w_full[s],
                                            c * CH, n0 + crank * my_rows, j, cmask);
                         else
-                            tma_load_3d(s_w + (size_t)s * W_BYTES, &tm_w, &w_full[s], c * CH, n0, j);
+                            tma_load_3d(s_w + (size_t)s * stage_bytes, &tm_w, &w_full[s], c * CH, n0, j);
                         if (++s == W_STAGES) { s = 0; ph ^= 1u; }
                     }
             }
@@ -376,10 +404,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;   // tl counts PROCESSED tiles (accumulator ring)
             uint64_t adesc = adesc_first, bstage = bdesc_first;
             uint32_t w_ready = 0;
-            for (int tile = cid; tile < p.total_tiles; tile += ncl) {
+            const int tps = p.tps;
+            const uint64_t a_stage_step = A_STAGE_STEP * (uint64_t)tps;
+            TileIter ti;
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch); ti.item < p.total_tiles; ti.next(ncl)) {
                 {
                     int n0m, i0m, bm;
-                    decode(tile, n0m, i0m, bm);
+                    decode(ti, n0m, i0m, bm);
                     if (!tile_live(i0m, bm)) continue;
                 }
                 const uint32_t buf = tl % ACC_STAGES;
@@ -392,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     mbar_wait(&act_full[sa], aph);
                     if (c == 0 && lane == 0) VTTS_TRACE(2);
                     uint64_t bdesc = bstage + (uint64_t)tap0;
-                    for (int j = 0; j < p.taps; ++j) {
+                    for (int j = 0; j < p.taps; j += tps) {
                         if (!w_ready) mbar_wait_addr(wfull0 + sw * 8u, wph);
                         tc_fence_after();
                         // next weight stage (after the very last step the probe simply reports "not ready")
@@ -407,6 +438,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                             }
                             __syncwarp();
                             w_ready = 0;
+                        } else if (tps == 2) {
+                            // second tap of the step; for an odd tap count its weights are TMA zero-fill, any row works
+                            const uint64_t bdesc1 = (j + 1 < p.taps) ? bdesc + (uint64_t)tap_step : bdesc;
+                            if (KSTEPS == 4)
+                                w_ready = umma_step4x2_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn,
+                                                            wempty0 + sw * 8u, bdesc1, A_STAGE_STEP);
+                            else
+                                w_ready = umma_step2x2_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn,
+                                                            wempty0 + sw * 8u, bdesc1, A_STAGE_STEP);
+                            bdesc += (uint64_t)tap_step;
                         } else if (KSTEPS == 4) {
                             w_ready = umma_step4_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
                         } else {
@@ -414,7 +455,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         }
                         acc = 1;
                         bdesc += (uint64_t)tap_step;
-                        adesc += A_STAGE_STEP;
+                        adesc += a_stage_step;
                         sw = sn; wph = pn;
                         if (sn == 0) adesc = adesc_first;
                     }
@@ -452,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one tile ahead,
         // spread over all epilogue threads
         const int et = threadIdx.x;                                // 0 .. EPI_WARPS*32-1
-        auto prefetch_tile = [&](int tile) {
+        auto prefetch_tile = [&](const TileIter &tile) {
             if (!(R || C) || !unit) return;
             int n0p, i0p, bp;
             decode(tile, n0p, i0p, bp);
@@ -470,13 +511,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 }
             }
         };
-        if (cid < p.total_tiles) prefetch_tile(cid);
+        TileIter ti, tnext;
+        ti.init(cid, ncl, p.m_blocks, p.groups_per_batch);
+        tnext = ti;
+        if (cid < p.total_tiles) prefetch_tile(ti);
+        // with a single m block and no per-batch bias the thread's bias never changes: load it once
+        const bool bias_fixed = p.m_blocks == 1 && p.bias_b == nullptr;
+        float bias_const = 0.f;
+        if (bias_fixed && p.bias && r_in_copy < p.n_total) bias_const = __ldg(p.bias + (r_in_copy % p.cout));
         uint32_t tl = 0;                                    // counts PROCESSED tiles (accumulator ring)
-        for (int tile = cid; tile < p.total_tiles; tile += ncl) {
-            if (tile + ncl < p.total_tiles) prefetch_tile(tile + ncl);
+        for (; ti.item < p.total_tiles; ti.next(ncl)) {
+            tnext.next(ncl);
+            if (tnext.item < p.total_tiles) prefetch_tile(tnext);
             if (quarter >= p.epi_quarters) continue;        // this warp's TMEM lanes never hold real rows: prefetch duty only
             int n0, i0, b;
-            decode(tile, n0, i0, b);
+            decode(ti, n0, i0, b);
             if (!tile_live(i0, b)) continue;
             const uint32_t buf = tl % ACC_STAGES;
             const int nq = n0 + (quarter % qpc) * 32;       // first output row of this warp
@@ -484,9 +533,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const bool row_ok = n < p.n_total;
             const int phase = nq / p.cout;                  // warp-uniform (cout is a multiple of 32)
             const int co = n - phase * p.cout;
-            float bias = 0.f;
-            if (row_ok && p.bias) bias = __ldg(p.bias + co);
-            if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
+            float bias = bias_const;
+            if (!bias_fixed) {
+                bias = 0.f;
+                if (row_ok && p.bias) bias = __ldg(p.bias + co);
+                if (row_ok && p.bias_b) bias = bias + __ldg(p.bias_b + (size_t)b * p.cout + co);
+            }
             const bool quarter_used = nq < p.n_total;       // warp-uniform
             const bool rows_full = nq + 32 <= p.n_total;    // warp-uniform
             const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
@@ -544,7 +596,7 @@ struct TcLaunch {
 
 static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
     return (size_t)act_stages * ACT_ROWS * rowb + (size_t)w_stages * TM * rowb +
-           (size_t)(2 * act_stages + 2 * w_stages + 2 * ACC_STAGES) * 8 + 16;
+           (size_t)(2 * act_stages + 2 * w_stages + 2 * ACC_STAGES) * 8 + 16 + MAX_TRIM_BATCH * sizeof(int);
 }
 
 static bool tc_cluster_enabled() {
@@ -619,9 +671,8 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     p.total_tiles = (int)total;
     // pipeline depths: narrow (HBM-bound) layers need many activation bytes in flight, wide
     // (tensor-bound) layers a deep weight pipeline
-    if (rowb == 64) { p.act_stages = 6; p.w_stages = 8; }
-    else if (p.chunks == 1) { p.act_stages = 4; p.w_stages = 4; }
-    else { p.act_stages = 2; p.w_stages = 8; }
+    p.batch = B;
+    if (p.lens && B > MAX_TRIM_BATCH) p.lens = nullptr;   // limits table is in shared memory
     // narrow layers (32 / 64 output rows): the packed weights repeat the rows 4x / 2x over the 128 lanes so
     // that every TMEM lane quarter (= every SM sub-partition's epilogue warps) holds a replica
     p.rep = (p.m_blocks == 1 && (p.n_total == 32 || p.n_total == 64)) ? TM / p.n_total : 1;
@@ -629,8 +680,13 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     // quarters that hold real rows in every tile (a partial last m-block keeps all warps in the handshake)
     p.epi_quarters = (p.rep == 1 && p.m_blocks == 1 && p.n_total < TM) ? (p.n_total + 31) / 32 : 4;
     p.L4 = (p.L_out + 3) / 4;
+    // single-chunk (narrow) layers: two taps per pipeline step (needs full 128-row weight tiles in the stage)
+    p.tps = (p.chunks == 1 && p.cluster == 1 && p.taps >= 2 && p.w_rows == TM) ? 2 : 1;
+    if (rowb == 64) { p.act_stages = 6; p.w_stages = 8 / p.tps; }
+    else if (p.chunks == 1) { p.act_stages = p.tps == 2 ? 3 : 4; p.w_stages = p.tps == 2 ? 3 : 4; }
+    else { p.act_stages = 2; p.w_stages = 8; }
     L.p = p;
-    L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages);
+    L.smem = tc_smem_bytes(rowb, p.act_stages, p.w_stages * p.tps);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc: %zu B shared memory", L.smem);
     const int sms = tc_num_sms();
     const int max_clusters = sms / p.cluster;
@@ -645,7 +701,7 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
     {
         uint64_t dims[3] = {(uint64_t)ci_pad, (uint64_t)n_pad, (uint64_t)p.taps};
         uint64_t str[2] = {(uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * (uint64_t)n_pad};
-        uint32_t box[3] = {(uint32_t)ch, (uint32_t)(p.w_rows / p.cluster), 1};
+        uint32_t box[3] = {(uint32_t)ch, (uint32_t)(p.w_rows / p.cluster), (uint32_t)p.tps};
         int rc = make_tmap_bf16(&L.tm_w, w, 3, dims, str, box, rowb);
         if (rc) return rc;
     }
@@ -1256,7 +1312,7 @@ extern "C" int vtts_dbg_trace(int enable, long long *host_out, int n) {
 extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const float *res, float *y,
                                   float *y_act, int B, int cin, int cout, int L, int ksize, int dilation,
                                   float slope_in, float slope_out, int fp16, vtts_stream_t stream) {
-    VTTS_REQUIRE(x && w && y, "vtts_dbg_conv1d_tc: null pointer");
+    VTTS_REQUIRE(x && w && (y || y_act), "vtts_dbg_conv1d_tc: null pointer");
     const int fmt = fp16 ? VTTS_FMT_FP16 : VTTS_FMT_BF16;
     cudaStream_t st = (cudaStream_t)stream;
     const int ci_pad = ci_pad_of(cin), n_pad = pad_to(cout, TM);
@@ -1278,7 +1334,7 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
     }
     if (!rc) {
         TcConvParams p{};
-        p.bias = bias; p.res = res ? rcl : nullptr; p.out_x = ox; p.out_a = y_act ? oa : nullptr; p.out_a_ld = cout;
+        p.bias = bias; p.res = res ? rcl : nullptr; p.out_x = y ? ox : nullptr; p.out_a = y_act ? oa : nullptr; p.out_a_ld = cout;
         p.slope_out = slope_out; p.n_total = cout; p.cout = cout; p.L_out = L; p.n_pos = L; p.out_stride = 1;
         p.out_off0 = 0; p.taps = ksize; p.tap_off0 = -(ksize - 1) / 2 * dilation; p.tap_step = dilation;
         p.trace = g_trace_on;
@@ -1286,7 +1342,7 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
         rc = tc_prepare(Lc, fmt, a, B, L, ci_pad, wp, n_pad, p);
         if (!rc) rc = tc_launch(Lc, st);
     }
-    if (!rc) rc = launch_tp4_to_cf(ox, y, B, cout, L, st);
+    if (!rc && y) rc = launch_tp4_to_cf(ox, y, B, cout, L, st);
     if (!rc && y_act) rc = launch_cl_16_to_cf_f32(oa, y_act, B, cout, L, cout, fmt, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(a); cudaFree(wp); cudaFree(oa); cudaFree(ox); cudaFree(rcl);

@@ -275,6 +275,68 @@ __device__ __forceinline__ uint32_t umma_step2_warp(uint32_t tmem_d, uint64_t a0
         : "memory");
     return ready;
 }
+// Two taps per step (narrow layers): the weight stage holds two consecutive tap tiles (tap stride a_tap_step),
+// b1 is the activation descriptor of the second tap.  Halves the per-MMA barrier/commit overhead.
+__device__ __forceinline__ uint32_t umma_step2x2_warp(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
+                                                    uint32_t acc_first, uint32_t next_full_addr, uint32_t next_parity,
+                                                    uint32_t this_empty_addr, uint64_t b1, uint64_t a_tap_step) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, e;\n\t.reg .b64 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, %10;\n\tadd.u64 a, a, 0;\n\tadd.u64 b, %9, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, %10;\n\tadd.u64 a, a, 2;\n\tadd.u64 b, %9, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(next_full_addr), "r"(next_parity),
+          "r"(this_empty_addr), "l"(b1), "l"(a_tap_step)
+        : "memory");
+    return ready;
+}
+// Two taps per step (narrow layers): the weight stage holds two consecutive tap tiles (tap stride a_tap_step),
+// b1 is the activation descriptor of the second tap.  Halves the per-MMA barrier/commit overhead.
+__device__ __forceinline__ uint32_t umma_step4x2_warp(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc,
+                                                    uint32_t acc_first, uint32_t next_full_addr, uint32_t next_parity,
+                                                    uint32_t this_empty_addr, uint64_t b1, uint64_t a_tap_step) {
+    uint32_t ready;
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, e;\n\t.reg .b64 a, b;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%6], %7;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, p;\n\t"
+        "add.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, %10;\n\tadd.u64 a, a, 0;\n\tadd.u64 b, %9, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, %10;\n\tadd.u64 a, a, 2;\n\tadd.u64 b, %9, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, %10;\n\tadd.u64 a, a, 4;\n\tadd.u64 b, %9, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "add.u64 a, %2, %10;\n\tadd.u64 a, a, 6;\n\tadd.u64 b, %9, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %4, t;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first), "r"(next_full_addr), "r"(next_parity),
+          "r"(this_empty_addr), "l"(b1), "l"(a_tap_step)
+        : "memory");
+    return ready;
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {   // whole converged warp; one lane commits
     asm volatile(
         "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
