@@ -214,6 +214,22 @@ __device__ __forceinline__ void epi_group16_edge(const uint32_t (&v)[16], float 
     }
 }
 
+// Fully valid 16-column group of a polyphase upsample (out_stride > 1; writes fp32 x and the 16-bit copy, no
+// residual): cheap 32-bit index arithmetic relative to per-batch base pointers, no per-element bounds checks.
+template <int FMT>
+__device__ __forceinline__ void epi_group16_poly(const uint32_t (&v)[16], float bias, const TcConvParams &p,
+                                                 float *px_b /* out_x + (b*L4*C + co)*4 */,
+                                                 uint16_t *pa_b /* out_a + b*L_out*lda + co */, int t_first) {
+    const int C4 = p.cout * 4;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int t = t_first + e * p.out_stride;
+        const float val = __uint_as_float(v[e]) + bias;
+        px_b[(t >> 2) * C4 + (t & 3)] = val;
+        pa_b[t * p.out_a_ld] = cvt16(lrelu_max(val, p.slope_out), FMT);
+    }
+}
+
 template <int FMT, int MODE>
 __device__ __forceinline__ void epi_group16_c(int c_ct, const uint32_t (&v)[16], float bias, const TcConvParams &p,
                                               const EpiLoads &res, float *px, uint16_t *pa) {
@@ -490,6 +506,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                        : (R && C && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
         const bool unit = p.out_stride == 1 && p.out_off0 == 0 && p.n_total == p.cout && mode != EPI_GENERIC;
         const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
+        // polyphase upsample: fp32 x + 16-bit copy, nothing read; 32-bit index math is safe below 2^31 elements per row
+        const bool poly = !R && !C && !D && X && A && p.out_stride > 1 && (long long)p.L4 * p.cout * 4 < 0x7fffffffLL &&
+                          (long long)p.L_out * p.out_a_ld < 0x7fffffffLL;
         // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one tile ahead,
         // spread over all epilogue threads
         const int et = threadIdx.x;                                // 0 .. EPI_WARPS*32-1
@@ -531,7 +550,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int nq = n0 + (quarter % qpc) * 32;       // first output row of this warp
             const int n = n0 + r_in_copy;                   // global output row of this thread
             const bool row_ok = n < p.n_total;
-            const int phase = nq / p.cout;                  // warp-uniform (cout is a multiple of 32)
+            const int phase = p.n_total == p.cout ? 0 : nq / p.cout;   // warp-uniform (cout is a multiple of 32)
             const int co = n - phase * p.cout;
             float bias = bias_const;
             if (!bias_fixed) {
@@ -567,6 +586,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         float *px = X ? p.out_x + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + co) * 4 : nullptr;
                         uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + ibase) * p.out_a_ld + co : nullptr;
                         epi_group16_dispatch<FMT>(mode, c_ct, v, bias, p, cur, px, pa);
+                    } else if (poly && rows_full && ibase + 16 <= p.n_pos &&
+                               (long long)ibase * p.out_stride + p.out_off0 + phase >= 0 &&
+                               (long long)(ibase + 15) * p.out_stride + p.out_off0 + phase < p.L_out) {
+                        epi_group16_poly<FMT>(v, bias, p, p.out_x + ((long long)b * p.L4 * p.cout + co) * 4,
+                                              p.out_a + (long long)b * p.L_out * p.out_a_ld + co,
+                                              ibase * p.out_stride + p.out_off0 + phase);
                     } else {
                         epi_group16_edge<FMT>(v, bias, p, row_ok, b, ibase, phase, co);
                     }
