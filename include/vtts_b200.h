@@ -67,6 +67,17 @@ int vtts_lr_gather(const void *xs, const int64_t *ds, void *out, int B, int Tmax
                    int64_t T_out, int elem_size, const void *pad, vtts_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GaussianUpsampling -- replaces models/tts/fastspeech2/layers.py:476-520 (GaussianUpsampling.forward;
+ * same body in models/gan_tts/jets/alignments.py:168-222).  hs (B,T_text,D) fp32, ds (B,T_text) int64,
+ * h_mask (B,T_feats) / d_mask (B,T_text) torch.bool bytes or NULL, out (B,T_feats,D) fp32.
+ * The all-zero-batch fix-up (layers.py:492-499) and T_feats (layers.py:501-504) are the host's job
+ * (vtts_lr_rowsum / vtts_lr_fix_zero_rows).
+ * ---------------------------------------------------------------------------------------- */
+int vtts_gauss_upsample(const float *hs, const int64_t *ds, const unsigned char *h_mask,
+                        const unsigned char *d_mask, float *out, int B, int T_text, int D, int T_feats,
+                        float delta, vtts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * HiFi-GAN generator -- replaces models/gan_tts/hifigan/generator.py:132-156
  * (HiFiGAN.forward), layers.py:83-98 (ResidualBlock.forward) and the vits2 skin
  * models/gan_tts/vits2/layers.py:159-177 (Generator.forward), sublayers.py:293-303,341-349.

@@ -117,3 +117,11 @@ def load_length_regulator():
         layers = _load_file("models.tts.fastspeech2.layers", "models/tts/fastspeech2/layers.py")
         LengthRegulator = layers.LengthRegulator
     return LengthRegulator
+
+
+def load_gaussian_upsampling():
+    """Return the reference ``GaussianUpsampling`` class (fastspeech2/layers.py:465-520)."""
+    load_length_regulator()
+    import sys as _sys
+
+    return _sys.modules["models.tts.fastspeech2.layers"].GaussianUpsampling

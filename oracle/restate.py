@@ -277,3 +277,34 @@ def make_hifigan_state_dict(
     if global_channels > 0:
         conv("global_conv", channels, global_channels, 1)
     return sd
+
+
+# --------------------------------------------------------------------------------------------
+# GaussianUpsampling  (models/tts/fastspeech2/layers.py:465-520; same body in jets/alignments.py:168-222)
+# --------------------------------------------------------------------------------------------
+
+
+def gaussian_upsampling(hs: torch.Tensor, ds: torch.Tensor, h_masks: Optional[torch.Tensor] = None,
+                        d_masks: Optional[torch.Tensor] = None, delta: float = 0.1):
+    """Restates ``GaussianUpsampling.forward`` (layers.py:476-520) with explicit fp32 steps.
+
+    ``ds`` is mutated in place on the all-zero-batch path (layers.py:492-499).  Without ``h_masks`` the
+    number of output frames is the duration sum over the WHOLE batch (layers.py:501-502) -- a reference
+    quirk that is preserved, not fixed.  Returns (B, T_feats, adim).
+    """
+    B = ds.size(0)
+    if int(ds.sum()) == 0:
+        logging.warning(
+            "predicted durations includes all 0 sequences. fill the first element with 1."
+        )
+        ds[ds.sum(dim=1).eq(0)] = 1
+    T_feats = int(ds.sum()) if h_masks is None else h_masks.size(-1)
+    t = torch.arange(0, T_feats).unsqueeze(0).repeat(B, 1).float()          # layers.py:505
+    if h_masks is not None:
+        t = t * h_masks.float()                                             # layers.py:506-507
+    c = ds.cumsum(dim=-1).float() - ds.float() / 2                          # layers.py:509 (int64 - float32 -> float32)
+    energy = (-1 * delta) * (t.unsqueeze(-1) - c.unsqueeze(1)) ** 2         # layers.py:510
+    if d_masks is not None:
+        energy = energy.masked_fill(~(d_masks.unsqueeze(1).repeat(1, T_feats, 1)), -float("inf"))
+    p_attn = torch.softmax(energy, dim=2)                                   # layers.py:516
+    return torch.matmul(p_attn, hs.float())                                 # layers.py:517

@@ -140,8 +140,42 @@ def vits2_small():
     print("vits2_small ok")
 
 
+def gaussian_cases():
+    GU = ref_loader.load_gaussian_upsampling()
+    g = torch.Generator().manual_seed(3)
+    out = {}
+
+    def add(name, hs, ds, h_masks=None, d_masks=None, delta=0.1):
+        ds_work = ds.clone()
+        y = GU(delta=delta)(hs, ds_work, h_masks, d_masks)
+        out[f"{name}.hs"] = hs.numpy(); out[f"{name}.ds"] = ds.numpy(); out[f"{name}.ds_after"] = ds_work.numpy()
+        out[f"{name}.y"] = y.numpy(); out[f"{name}.delta"] = np.float64(delta)
+        if h_masks is not None: out[f"{name}.h_masks"] = h_masks.numpy()
+        if d_masks is not None: out[f"{name}.d_masks"] = d_masks.numpy()
+
+    # the VarianceAdaptor call (layers.py:231): h_masks = ~mel_mask, d_masks = ~txt_mask
+    B, T, D = 3, 11, 48
+    tl = torch.tensor([11, 7, 4])
+    ds = torch.randint(1, 6, (B, T), generator=g)
+    ds[torch.arange(T)[None] >= tl[:, None]] = 0
+    ml = ds.sum(1)
+    h = torch.arange(int(ml.max()))[None] < ml[:, None]
+    d = torch.arange(T)[None] < tl[:, None]
+    add("masked", torch.randn(B, T, D, generator=g), ds, h, d)
+    # no masks: T_feats = sum over the WHOLE batch (quirk)
+    add("nomask", torch.randn(2, 5, 16, generator=g), torch.randint(0, 4, (2, 5), generator=g))
+    # zero durations inside rows, other delta, D not a multiple of 32
+    ds2 = torch.tensor([[0, 3, 0, 2, 1], [2, 0, 0, 0, 4]])
+    add("zeros", torch.randn(2, 5, 37, generator=g), ds2, torch.ones(2, 9, dtype=torch.bool), torch.ones(2, 5, dtype=torch.bool), delta=0.35)
+    # all-zero batch -> in-place fix-up
+    add("all_zero", torch.randn(2, 4, 8, generator=g), torch.zeros(2, 4, dtype=torch.long), torch.ones(2, 4, dtype=torch.bool), None)
+    np.savez_compressed(os.path.join(OUT, "gaussian_cases.npz"), **out)
+    print("gaussian_cases ok")
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs /root/reference"
+    gaussian_cases()
     lr_cases()
     hifigan_small()
     hifigan_v1()

@@ -7,6 +7,7 @@ reference's ``state_dict`` keys, ctypes calls, batch sharding across ranks.
 """
 from . import _lib
 from .dropin import install, uninstall
+from .gaussian_upsampling import GaussianUpsampling
 from .hifigan import HiFiGAN, ResidualBlock
 from .length_regulator import LengthRegulator
 from .sharding import gather_waveforms, plan_shards, shard_batch
@@ -14,7 +15,7 @@ from .synthesis import Synthesizer
 from .vits2 import Generator, ResBlock1, ResBlock2
 
 __all__ = [
-    "HiFiGAN", "ResidualBlock", "LengthRegulator", "Generator", "ResBlock1", "ResBlock2",
+    "HiFiGAN", "ResidualBlock", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
     "Synthesizer", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall",
 ]
 __version__ = "0.1.0"

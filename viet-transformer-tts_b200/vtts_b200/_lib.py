@@ -44,6 +44,8 @@ SIGNATURES = {
     "vtts_lr_fix_zero_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtts_lr_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64,
                                  C.c_int, C.c_void_p, C.c_void_p]),
+    "vtts_gauss_upsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "vtts_gen_create": (C.c_int, [C.POINTER(VttsGenConfig), C.POINTER(C.c_void_p)]),
     "vtts_gen_destroy": (C.c_int, [C.c_void_p]),
     "vtts_gen_num_layers": (C.c_int, [C.c_void_p]),

@@ -9,7 +9,7 @@
 Replaced symbols (reference file:line):
   models/gan_tts/hifigan/generator.py:16   HiFiGAN
   models/gan_tts/hifigan/layers.py:16      ResidualBlock
-  models/tts/fastspeech2/layers.py:410     LengthRegulator
+  models/tts/fastspeech2/layers.py:410     LengthRegulator      :465 GaussianUpsampling
   models/gan_tts/vits2/layers.py:107       Generator
   models/gan_tts/vits2/sublayers.py:215    ResBlock1      :312 ResBlock2
 Every module already imported that holds a reference to one of the original classes (e.g.
@@ -24,7 +24,8 @@ from typing import Dict, Tuple
 _TARGETS = {
     "models.gan_tts.hifigan.generator": ("HiFiGAN",),
     "models.gan_tts.hifigan.layers": ("ResidualBlock",),
-    "models.tts.fastspeech2.layers": ("LengthRegulator",),
+    "models.tts.fastspeech2.layers": ("LengthRegulator", "GaussianUpsampling"),
+    "models.gan_tts.jets.alignments": ("GaussianUpsampling",),
     "models.gan_tts.vits2.layers": ("Generator",),
     "models.gan_tts.vits2.sublayers": ("ResBlock1", "ResBlock2"),
 }
@@ -32,11 +33,12 @@ _saved: Dict[Tuple[str, str], object] = {}
 
 
 def _replacements():
-    from . import hifigan, length_regulator, vits2
+    from . import gaussian_upsampling, hifigan, length_regulator, vits2
 
     return {
         "HiFiGAN": hifigan.HiFiGAN, "ResidualBlock": hifigan.ResidualBlock,
         "LengthRegulator": length_regulator.LengthRegulator, "Generator": vits2.Generator,
+        "GaussianUpsampling": gaussian_upsampling.GaussianUpsampling,
         "ResBlock1": vits2.ResBlock1, "ResBlock2": vits2.ResBlock2,
     }
 

@@ -1,0 +1,59 @@
+"""Drop-in ``GaussianUpsampling`` backed by csrc/gauss.cu.
+
+Mirrors ``models/tts/fastspeech2/layers.py:465-520`` (and the identical class in
+``models/gan_tts/jets/alignments.py:168-222``): same constructor and ``forward(hs, ds, h_masks, d_masks)``,
+including the in-place all-zero-batch fix-up of ``ds`` and the reference quirk that without ``h_masks`` the
+number of output frames is the duration sum over the WHOLE batch.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianUpsampling(nn.Module):
+    """Gaussian upsampling with fixed temperature (https://arxiv.org/abs/2010.04301)."""
+
+    def __init__(self, delta: float = 0.1):
+        super().__init__()
+        self.delta = delta
+
+    def forward(self, hs: torch.Tensor, ds: torch.Tensor, h_masks: Optional[torch.Tensor] = None,
+                d_masks: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """hs (B,T_text,adim), ds (B,T_text), h_masks (B,T_feats) bool, d_masks (B,T_text) bool -> (B,T_feats,adim)."""
+        lib = _lib.load()
+        if not hs.is_cuda or not ds.is_cuda:
+            raise RuntimeError("vtts_b200.GaussianUpsampling: inputs must be CUDA tensors (no CPU fallback)")
+        if hs.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("vtts_b200.GaussianUpsampling: synthesis only (backward is not implemented)")
+        B, T_text, D = hs.shape
+        dev = hs.device
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(dev)
+            ds_k = ds if (ds.dtype == torch.int64 and ds.is_contiguous()) else ds.to(torch.int64).contiguous()
+            need_total = h_masks is None
+            stats = torch.empty(3, dtype=torch.int64, device=dev)
+            _lib.check(lib.vtts_lr_rowsum(ds_k.data_ptr(), B, T_text, 0, stats.data_ptr(), stream))
+            # `if ds.sum() == 0` (layers.py:492) needs the value on the host, exactly like the reference
+            _, total, _ = stats.tolist()
+            if total == 0:
+                logging.warning(
+                    "predicted durations includes all 0 sequences. fill the first element with 1."
+                )
+                _lib.check(lib.vtts_lr_fix_zero_rows(ds_k.data_ptr(), B, T_text, stream))
+                if ds_k is not ds:
+                    ds.copy_(ds_k.to(ds.dtype))
+                total = B * T_text
+            T_feats = int(total) if need_total else int(h_masks.size(-1))
+            hs_k = hs.detach().to(torch.float32).contiguous()
+            hm = None if h_masks is None else h_masks.to(dev, torch.bool).contiguous()
+            dm = None if d_masks is None else d_masks.to(dev, torch.bool).contiguous()
+            out = torch.empty((B, T_feats, D), dtype=torch.float32, device=dev)
+            _lib.check(lib.vtts_gauss_upsample(hs_k.data_ptr(), ds_k.data_ptr(), _lib.ptr(hm), _lib.ptr(dm), out.data_ptr(),
+                                               B, T_text, D, T_feats, float(self.delta), stream))
+        return out if hs.dtype == torch.float32 else out.to(hs.dtype)
