@@ -348,7 +348,7 @@ def main():
                     "h2d_bytes_per_step": hs.numel() * 4 + ds.numel() * 8,
                     "d2h_bytes_per_step": int(wav.numel()) * 4 + ds.shape[0] * 8,
                     "ms_per_step": e2e_ms_all / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps * world,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                          "frac": achieved / tc_peak, "traffic": None,
                          "kernel": "generator conv kernels (all launches of one forward)",

@@ -191,3 +191,22 @@ def test_synthesizer_trim_matches_untrimmed_on_valid_audio():
     for b in range(4):
         n = int(len_t[b])
         assert torch.equal(wav_t[b, :, :n], wav_f[b, :, :n])
+
+
+@pytest.mark.parametrize("B,T", [(4, 1000), (1, 2000), (64, 100)])
+def test_baseline_config_shapes_fp16_vs_fp32_kernels(B, T):
+    """BASELINE.json configs 4/5 corners (long utterances, wide batch): fp16 tensor-core path vs the fp32
+    kernels (pinned to the oracle elsewhere), plus the size-independent row-independence property."""
+    m, _ = v1_model("fp16")
+    g = torch.Generator().manual_seed(B + T)
+    c = torch.randn(B, 80, T, generator=g).to(DEV)
+    with torch.no_grad():
+        y = m(c)
+        m.precision = "fp32"
+        ref = m(c)
+        m.precision = "fp16"
+        y_last = m(c[-1:])
+    assert y.shape == (B, 1, T * 256)
+    assert rel_l2(y, ref) <= BF16_REL and max_abs(y, ref) <= BF16_MAXABS
+    assert max_abs(y[-1:], y_last) < 1e-6
+    assert bool(torch.isfinite(y).all())
