@@ -734,6 +734,378 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused ResidualBlock unit:  x_new = conv2(lrelu(conv1(a))) + x     (layers.py:93-97, one (convs1[i], convs2[i]) pair)
+//
+// Same persistent warp-specialised structure as conv_tc_kernel, but a tile runs two GEMM phases and the
+// intermediate xt never leaves the SM: phase A (conv1, dilated) accumulates 256 positions into TMEM
+// accumulator A; the epilogue warps turn it into the 16-bit LeakyReLU'd operand and write it straight into a
+// swizzled shared-memory tile (zero outside [0, L): conv2 pads ITS input with zeros);
+// phase B (conv2, dilation 1) reads that tile through row-shifted descriptors and accumulates 240 positions
+// into accumulator B, which gets the usual fused epilogue (bias, residual, MRF sum/mean, 16-bit copy).
+// Saves the xt round trip through HBM (4 of the 16 bytes per element of a unit), one launch and one tile pass.
+// ---------------------------------------------------------------------------------------------
+constexpr int UN2 = 240;           // conv2 output positions per tile (UMMA N of phase B)
+constexpr int UXT_OFF = 8;         // xt row 0 is position i0 - 8 (covers conv2 half-widths up to 8)
+
+struct TcUnitParams {
+    TcConvParams e;                // phase-B epilogue + shared geometry (taps/tap_off0/tap_step describe conv1)
+    const float *bias1;            // conv1 bias (C) or null
+    float slope_mid;               // LeakyReLU between conv1 and conv2
+    int taps2;                     // conv2 taps (dilation 1)
+    int xt_chunks;                 // C / chunk channels
+};
+
+template <int ROWB, int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w1,
+               const __grid_constant__ CUtensorMap tm_w2, const TcUnitParams u) {
+    const TcConvParams &p = u.e;
+    constexpr int CH = ROWB / 2;
+    constexpr int KSTEPS = CH / 16;
+    constexpr int ACT_BYTES = ACT_ROWS * ROWB;
+    constexpr int W_BYTES = TM * ROWB;
+    constexpr int XT_BYTES = TN * ROWB;          // one 64/32-channel chunk of the xt tile
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("vtts: smem base not 1024-byte aligned\n"); __trap(); }
+    const uint32_t ACT_STAGES = (uint32_t)p.act_stages, W_STAGES = (uint32_t)p.w_stages;
+    uint8_t *s_act = smem;
+    uint8_t *s_w = s_act + (size_t)ACT_STAGES * ACT_BYTES;
+    uint8_t *s_xt = s_w + (size_t)W_STAGES * W_BYTES * p.tps;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + (size_t)u.xt_chunks * XT_BYTES);
+    uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
+    uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
+    uint64_t *accA_full = w_empty + W_STAGES, *xt_full = accA_full + 1, *accB_full = xt_full + 1, *accB_empty = accB_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 1);
+    int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
+    const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
+    const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
+    const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
+    const int h2 = (u.taps2 - 1) / 2;
+    const int ncta = (int)gridDim.x;
+    const int n_epi = p.epi_quarters * (EPI_WARPS / 4);   // participating epilogue warps
+
+    // work items: (time tile of UN2 outputs, batch); m_blocks == 1
+    auto tile_i0 = [&](int item, int &i0, int &b) { b = item / p.t_tiles; i0 = (item - b * p.t_tiles) * UN2; };
+    const bool trimming = p.lens != nullptr;
+    auto tile_live = [&](int i0, int b) -> bool { return !trimming || i0 < s_lim[b]; };
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
+        for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        mbar_init(accA_full, 1); mbar_init(xt_full, (uint32_t)n_epi);
+        mbar_init(accB_full, 1); mbar_init(accB_empty, (uint32_t)n_epi);
+        fence_barrier_init();
+    }
+    constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2;
+    if (warp == WARP_MMA) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (p.lens != nullptr)
+        for (int i = threadIdx.x; i < p.batch; i += blockDim.x) {
+            const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate + p.len_extra;
+            s_lim[i] = lim > 0x7fffffffLL ? 0x7fffffff : (int)lim;
+        }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tps = p.tps;
+
+    if (warp == WARP_ACT) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_act);
+            uint32_t s = 0, ph = 0;
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(&act_empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
+                    for (int bx = 0; bx < nbox; ++bx)
+                        tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s],
+                                    c * CH, i0 - UXT_OFF + min_off + bx * BOX_ROWS, b);
+                    if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == WARP_W) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_w1);
+            tma_prefetch_desc(&tm_w2);
+            uint32_t s = 0, ph = 0;
+            const size_t stage_bytes = (size_t)W_BYTES * tps;
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+                for (int phase = 0; phase < 2; ++phase) {
+                    const CUtensorMap *tm = phase == 0 ? &tm_w1 : &tm_w2;
+                    const int ntaps = phase == 0 ? p.taps : u.taps2;
+                    for (int c = 0; c < p.chunks; ++c)
+                        for (int j = 0; j < ntaps; j += tps) {
+                            mbar_wait(&w_empty[s], ph ^ 1u);
+                            mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));
+                            tma_load_3d(s_w + (size_t)s * stage_bytes, tm, &w_full[s], c * CH, 0, j);
+                            if (++s == W_STAGES) { s = 0; ph ^= 1u; }
+                        }
+                }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // whole warp converged; elect.sync inside the step picks the issuing lane
+        constexpr uint32_t idescA = make_idesc_16(TM, TN, FMT), idescB = make_idesc_16(TM, UN2, FMT);
+        const uint32_t wfull0 = smem_u32(w_full), wempty0 = smem_u32(w_empty);
+        const uint64_t adesc_first = make_smem_desc(smem_u32(s_w), ROWB, 0);
+        const uint64_t bdesc_first = make_smem_desc(smem_u32(s_act), ROWB, 0);
+        const uint64_t xdesc_first = make_smem_desc(smem_u32(s_xt), ROWB, 0);
+        constexpr uint64_t A_STAGE_STEP = (uint64_t)(W_BYTES >> 4), B_STAGE_STEP = (uint64_t)(ACT_BYTES >> 4),
+                           X_CHUNK_STEP = (uint64_t)(XT_BYTES >> 4);
+        const uint64_t a_stage_step = A_STAGE_STEP * (uint64_t)tps;
+        const long long tap0 = (long long)(p.tap_off0 - min_off) * (ROWB >> 4);
+        const long long tap_step = (long long)p.tap_step * (ROWB >> 4);
+        const uint64_t xtap0 = (uint64_t)((UXT_OFF - h2) * (ROWB >> 4));   // conv2 tap 0 row, 16-byte units
+        constexpr uint64_t XTAP_STEP = (uint64_t)(ROWB >> 4);
+        uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;
+        uint64_t adesc = adesc_first, bstage = bdesc_first;
+        uint32_t w_ready = 0;
+        auto step = [&](uint32_t tmem_d, uint64_t bdesc, uint64_t bdesc1, uint32_t idesc, uint32_t acc) {
+            if (!w_ready) mbar_wait_addr(wfull0 + sw * 8u, wph);
+            tc_fence_after();
+            uint32_t sn = sw + 1, pn = wph;
+            if (sn == W_STAGES) { sn = 0; pn ^= 1u; }
+            if (tps == 2) {
+                if (KSTEPS == 4) w_ready = umma_step4x2_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u, bdesc1, A_STAGE_STEP);
+                else w_ready = umma_step2x2_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u, bdesc1, A_STAGE_STEP);
+            } else {
+                if (KSTEPS == 4) w_ready = umma_step4_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
+                else w_ready = umma_step2_warp(tmem_d, adesc, bdesc, idesc, acc, wfull0 + sn * 8u, pn, wempty0 + sw * 8u);
+            }
+            adesc += a_stage_step;
+            sw = sn; wph = pn;
+            if (sn == 0) adesc = adesc_first;
+        };
+        for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+            {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+            }
+            // ---- phase A: conv1 -> accumulator A (columns 0..255).  A is free: xt_full of the previous tile was
+            // observed before its phase B was issued, i.e. every epilogue warp had finished reading A.
+            uint32_t acc = 0;
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(&act_full[sa], aph);
+                uint64_t bdesc = bstage + (uint64_t)tap0;
+                for (int j = 0; j < p.taps; j += tps) {
+                    const uint64_t bdesc1 = (j + 1 < p.taps) ? bdesc + (uint64_t)tap_step : bdesc;
+                    step(tmem_base, bdesc, bdesc1, idescA, acc);
+                    acc = 1;
+                    bdesc += (uint64_t)(tap_step * tps);
+                }
+                umma_commit_elect(&act_empty[sa]);
+                bstage += B_STAGE_STEP;
+                if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; bstage = bdesc_first; }
+            }
+            umma_commit_elect(accA_full);
+            // ---- phase B: conv2 on the xt tile -> accumulator B (columns 256..495)
+            mbar_wait(xt_full, tl & 1u);                      // epilogue wrote the operand tile (and drained A)
+            mbar_wait(accB_empty, (tl & 1u) ^ 1u);            // previous tile's output epilogue drained B
+            tc_fence_after();
+            acc = 0;
+            uint64_t xchunk = xdesc_first;
+            for (int c = 0; c < p.chunks; ++c) {
+                uint64_t xdesc = xchunk + xtap0;
+                for (int j = 0; j < u.taps2; j += tps) {
+                    const uint64_t xdesc1 = (j + 1 < u.taps2) ? xdesc + XTAP_STEP : xdesc;
+                    step(tmem_base + TN, xdesc, xdesc1, idescB, acc);
+                    acc = 1;
+                    xdesc += XTAP_STEP * (uint64_t)tps;
+                }
+                xchunk += X_CHUNK_STEP;
+            }
+            umma_commit_elect(accB_full);
+            ++tl;
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int ew = warp, quarter = warp & 3;
+        constexpr int SHARERS = EPI_WARPS / 4;
+        const int qpc = 4 / p.rep;
+        const int worker = (quarter / qpc) * SHARERS + (ew / 4);      // which slice of the 16-column groups
+        const int n_workers = p.rep * SHARERS;
+        const int ch = (quarter % qpc) * 32 + lane;                  // channel of this thread (m_blocks == 1)
+        const bool row_ok = ch < p.n_total;
+        const bool rows_full = (quarter % qpc) * 32 + 32 <= p.n_total;
+        const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
+                   A = p.out_a != nullptr;
+        const int mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX
+                       : (R && Cc && !D && X && !A) ? EPI_RCX : (R && Cc && D && X && A) ? EPI_RCDXA
+                       : (R && Cc && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
+        const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
+        const float bias1 = (row_ok && u.bias1) ? __ldg(u.bias1 + ch) : 0.f;
+        const float bias2 = (row_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
+        // swizzled xt address pieces of this thread's channel
+        const int kc = ch % CH;
+        uint8_t *xt_ch = s_xt + (size_t)(ch / CH) * XT_BYTES + (kc & 7) * 2;
+        const int kchunk = kc >> 3;
+        const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
+        uint32_t tl = 0;
+        if (quarter < p.epi_quarters) {
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+                // residual loads of this warp's first output group go out before any waiting
+                EpiLoads cur{}, nxt{};
+                auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
+                auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4; };
+                if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout);
+                // ---- epilogue A: accumulator A -> 16-bit LeakyReLU'd conv2 operand in shared memory
+                mbar_wait_relaxed(accA_full, tl & 1u);
+                tc_fence_after();
+                for (int col = worker * 16; col < TN; col += n_workers * 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int r = col + e;
+                            const int pos = i0 - UXT_OFF + r;
+                            float val = lrelu_max(__uint_as_float(v[e]) + bias1, u.slope_mid);
+                            if (pos < 0 || pos >= p.n_pos) val = 0.f;      // conv2 zero-pads its own input
+                            const int swz = ROWB == 128 ? (r & 7) : ((r >> 1) & 3);
+                            *reinterpret_cast<uint16_t *>(xt_ch + (size_t)r * ROWB + ((kchunk ^ swz) << 4)) = cvt16(val, FMT);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xt_full);
+                // ---- epilogue B: accumulator B -> fused output epilogue
+                mbar_wait_relaxed(accB_full, tl & 1u);
+                tc_fence_after();
+                for (int col = worker * 16; col < UN2; col += n_workers * 16) {
+                    const int ibase = i0 + col;
+                    if (ibase >= p.n_pos) break;
+                    uint32_t v[16];
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(TN + col), v);
+                    cur = nxt;
+                    const bool fast = group_fast(ibase);
+                    const int col_n = col + n_workers * 16;
+                    if (R && col_n < UN2 && group_fast(i0 + col_n)) epi_load16<0>(nxt, res_ptr(i0 + col_n), p.cout);
+                    tmem_ld_wait();
+                    if (fast) {
+                        float *px = X ? p.out_x + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4 : nullptr;
+                        uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + ibase) * p.out_a_ld + ch : nullptr;
+                        epi_group16_dispatch<FMT>(mode, c_ct, v, bias2, p, cur, px, pa);
+                    } else {
+                        epi_group16_edge<FMT>(v, bias2, p, row_ok, b, ibase, 0, ch);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(accB_empty);
+                ++tl;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+struct TcUnitLaunch {
+    CUtensorMap tm_act, tm_w1, tm_w2;
+    TcUnitParams u;
+    int rowb, fmt;
+    dim3 grid;
+    size_t smem;
+};
+
+template <int ROWB, int FMT>
+static int unit_launch_t(const TcUnitLaunch &L, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    unit_tc_kernel<ROWB, FMT><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w1, L.tm_w2, L.u);
+    VTTS_CHECK_LAUNCH();
+    return VTTS_OK;
+}
+
+static bool tc_fuse_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VTTS_TC_FUSE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+// Can (conv1, conv2) of one unit run fused?  C in {32, 64, 128}, conv2 dilation 1 and half-width <= UXT_OFF.
+static bool unit_fusable(int C, int k1, int d1, int k2) {
+    if (!tc_fuse_enabled()) return false;
+    if (C != 32 && C != 64 && C != 128) return false;
+    if ((k1 - 1) * d1 > HALO_MAX || (k2 - 1) / 2 > UXT_OFF || k2 < 1) return false;
+    return true;
+}
+
+// act: (B, L, C) 16-bit operand of conv1; w1/w2: packed [taps][128][C]; p: phase-B epilogue (res/out_x/out_a/...).
+static int unit_prepare(TcUnitLaunch &L, int fmt, const uint16_t *act, int B, int Lpos, int C, const uint16_t *w1, int k1,
+                        int d1, const float *bias1, float slope_mid, const uint16_t *w2, int k2, TcConvParams p) {
+    const int rowb = (C % 64 == 0) ? 128 : 64;
+    const int ch = rowb / 2;
+    L.rowb = rowb; L.fmt = fmt;
+    p.n_total = C; p.cout = C; p.L_out = Lpos; p.n_pos = Lpos; p.out_stride = 1; p.out_off0 = 0;
+    p.taps = k1; p.tap_off0 = -(k1 - 1) / 2 * d1; p.tap_step = d1;
+    p.chunks = C / ch;
+    p.m_blocks = 1; p.cluster = 1; p.groups_per_batch = 0;
+    p.t_tiles = ceil_div(Lpos, UN2);
+    const long long total = (long long)p.t_tiles * B;
+    if (total > 0x7fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "tc: too many tiles");
+    p.total_tiles = (int)total;
+    p.inv_div = p.divide_by > 0.f ? 1.f / p.divide_by : 1.f;
+    p.rep = (C == 32 || C == 64) ? TM / C : 1;
+    p.w_rows = TM;
+    p.epi_quarters = 4;
+    p.L4 = (Lpos + 3) / 4;
+    p.batch = B;
+    if (p.lens && B > MAX_TRIM_BATCH) p.lens = nullptr;
+    p.tps = p.chunks == 1 ? 2 : 1;
+    if (rowb == 64) { p.act_stages = 4; p.w_stages = 4; }          // 80 + 64 + 16 KB
+    else if (p.chunks == 1) { p.act_stages = 2; p.w_stages = 3; }  // 80 + 96 + 32 KB
+    else { p.act_stages = 2; p.w_stages = 4; }                     // 80 + 64 + 64 KB
+    L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.xt_chunks = p.chunks;
+    L.smem = (size_t)p.act_stages * ACT_ROWS * rowb + (size_t)p.w_stages * p.tps * TM * rowb + (size_t)p.chunks * TN * rowb +
+             (size_t)(2 * p.act_stages + 2 * p.w_stages + 4) * 8 + 16 + MAX_TRIM_BATCH * sizeof(int);
+    if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc unit: %zu B shared memory", L.smem);
+    const int sms = tc_num_sms();
+    L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
+    {
+        uint64_t dims[3] = {(uint64_t)C, (uint64_t)Lpos, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * (uint64_t)Lpos};
+        uint32_t box[3] = {(uint32_t)ch, BOX_ROWS, 1};
+        int rc = make_tmap_bf16(&L.tm_act, act, 3, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    for (int w = 0; w < 2; ++w) {
+        uint64_t dims[3] = {(uint64_t)C, (uint64_t)TM, (uint64_t)(w == 0 ? k1 : k2)};
+        uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * (uint64_t)TM};
+        uint32_t box[3] = {(uint32_t)ch, TM, (uint32_t)p.tps};
+        int rc = make_tmap_bf16(w == 0 ? &L.tm_w1 : &L.tm_w2, w == 0 ? w1 : w2, 3, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    return VTTS_OK;
+}
+
+static int unit_launch(const TcUnitLaunch &L, cudaStream_t st) {
+    if (L.rowb == 128) return L.fmt == VTTS_FMT_BF16 ? unit_launch_t<128, 0>(L, st) : unit_launch_t<128, 1>(L, st);
+    return L.fmt == VTTS_FMT_BF16 ? unit_launch_t<64, 0>(L, st) : unit_launch_t<64, 1>(L, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight packing: fp32 reference layout -> bf16 [tap][n_pad][ci_pad]
 // ---------------------------------------------------------------------------------------------
 // Conv1d (cout,cin,k): n = co, tap j = kernel index.
@@ -1017,6 +1389,32 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
     h->launch_count++;
     return VTTS_OK;
 }
+// fused (conv1, conv2) unit of a ResidualBlock on the tensor cores
+static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const uint16_t *act, int B, int Lpos,
+                    TcConvParams p, float slope_mid, cudaStream_t st, int rate) {
+    p.bias = l2.has_bias ? l2.bias : nullptr;
+    if (h->trim_lens && rate > 0) {
+        p.lens = (const long long *)h->trim_lens;
+        p.len_margin = h->trim_margin;
+        p.len_rate = rate;
+        p.len_extra = 0;
+    }
+    TcUnitLaunch L;
+    int rc = unit_prepare(L, fmt, act, B, Lpos, l1.info.cout, l1.w16[fmt], l1.info.ksize, l1.info.dilation,
+                          l1.has_bias ? l1.bias : nullptr, slope_mid, l2.w16[fmt], l2.info.ksize, p);
+    if (rc) return rc;
+    ProfRec pr{};
+    if (prof_enabled()) {
+        cudaEventCreate(&pr.a); cudaEventCreate(&pr.b);
+        pr.kind = 2; pr.cin = l1.info.cin; pr.cout = l1.info.cout; pr.k = l1.info.ksize + l2.info.ksize; pr.d = l1.info.dilation;
+        pr.B = B; pr.L = Lpos;
+        cudaEventRecord(pr.a, st);
+    }
+    if ((rc = unit_launch(L, st))) return rc;
+    if (prof_enabled()) { cudaEventRecord(pr.b, st); g_prof.push_back(pr); }
+    h->launch_count++;
+    return VTTS_OK;
+}
 }  // namespace
 
 int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, int B, int T, void *workspace,
@@ -1093,7 +1491,9 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                 const Layer &l1 = h->layers[h->idx_c1[i][j][m]];
                 const Layer *fin = &l1;
                 const uint16_t *fin_in = ya;
-                if (cfg.use_additional_convs) {
+                const bool fuse = cfg.use_additional_convs &&
+                                  unit_fusable(C, l1.info.ksize, l1.info.dilation, h->layers[h->idx_c2[i][j][m]].info.ksize);
+                if (cfg.use_additional_convs && !fuse) {
                     TcConvParams p1{};  // xt = conv1(lrelu(x)); only its LeakyReLU'd bf16 copy is needed
                     p1.out_a = bf.a_t; p1.out_a_ld = C; p1.slope_out = cfg.lrelu_slope;
                     if ((rc = run_conv(h, fmt, l1, ya, B, Lo, Lo, p1, st, rate))) return rc;
@@ -1114,7 +1514,9 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                 } else {
                     p2.out_a = na; p2.out_a_ld = C; p2.slope_out = cfg.lrelu_slope;
                 }
-                if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st, rate))) return rc;
+                if (fuse) {
+                    if ((rc = run_unit(h, fmt, l1, h->layers[h->idx_c2[i][j][m]], ya, B, Lo, p2, cfg.lrelu_slope, st, rate))) return rc;
+                } else if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st, rate))) return rc;
                 yx = nx; ya = na;
             }
         }
