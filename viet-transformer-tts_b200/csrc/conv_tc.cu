@@ -785,7 +785,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
     const int h2 = (u.taps2 - 1) / 2;
     const int ncta = (int)gridDim.x;
-    const int n_epi = p.epi_quarters * (EPI_WARPS / 4);   // participating epilogue warps
+    const int n_epi = EPI_WARPS / 2;                      // warps per epilogue group (operand / output)
 
     // work items: (time tile of UN2 outputs, batch); m_blocks == 1
     auto tile_i0 = [&](int item, int &i0, int &b) { b = item / p.t_tiles; i0 = (item - b * p.t_tiles) * UN2; };
@@ -929,40 +929,28 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             ++tl;
         }
     } else {
-        // ===== epilogue warps =====
+        // ===== epilogue warps: two groups so that the operand epilogue of tile t+1 (accumulator A -> xt tile in
+        // shared memory, warps 0-7) overlaps the output epilogue of tile t (accumulator B -> HBM, warps 8-15) =====
         const int ew = warp, quarter = warp & 3;
-        constexpr int SHARERS = EPI_WARPS / 4;
+        const bool is_ea = ew < EPI_WARPS / 2;
+        constexpr int SHARERS = EPI_WARPS / 2 / 4;                   // warps per lane quarter within a group (2)
         const int qpc = 4 / p.rep;
-        const int worker = (quarter / qpc) * SHARERS + (ew / 4);      // which slice of the 16-column groups
+        const int worker = (quarter / qpc) * SHARERS + ((ew % (EPI_WARPS / 2)) / 4);   // slice of the 16-column groups
         const int n_workers = p.rep * SHARERS;
         const int ch = (quarter % qpc) * 32 + lane;                  // channel of this thread (m_blocks == 1)
         const bool row_ok = ch < p.n_total;
         const bool rows_full = (quarter % qpc) * 32 + 32 <= p.n_total;
-        const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
-                   A = p.out_a != nullptr;
-        const int mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX
-                       : (R && Cc && !D && X && !A) ? EPI_RCX : (R && Cc && D && X && A) ? EPI_RCDXA
-                       : (R && Cc && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
-        const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
-        const float bias1 = (row_ok && u.bias1) ? __ldg(u.bias1 + ch) : 0.f;
-        const float bias2 = (row_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
-        // swizzled xt address pieces of this thread's channel
-        const int kc = ch % CH;
-        uint8_t *xt_ch = s_xt + (size_t)(ch / CH) * XT_BYTES + (kc & 7) * 2;
-        const int kchunk = kc >> 3;
-        const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
         uint32_t tl = 0;
-        if (quarter < p.epi_quarters) {
+        if (is_ea) {
+            const float bias1 = (row_ok && u.bias1) ? __ldg(u.bias1 + ch) : 0.f;
+            // swizzled xt address pieces of this thread's channel
+            const int kc = ch % CH;
+            uint8_t *xt_ch = s_xt + (size_t)(ch / CH) * XT_BYTES + (kc & 7) * 2;
+            const int kchunk = kc >> 3;
             for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
-                // residual loads of this warp's first output group go out before any waiting
-                EpiLoads cur{}, nxt{};
-                auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
-                auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4; };
-                if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout);
-                // ---- epilogue A: accumulator A -> 16-bit LeakyReLU'd conv2 operand in shared memory
                 mbar_wait_relaxed(accA_full, tl & 1u);
                 tc_fence_after();
                 for (int col = worker * 16; col < TN; col += n_workers * 16) {
@@ -985,7 +973,26 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(xt_full);
-                // ---- epilogue B: accumulator B -> fused output epilogue
+                ++tl;
+            }
+        } else {
+            const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
+                       A = p.out_a != nullptr;
+            const int mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX
+                           : (R && Cc && !D && X && !A) ? EPI_RCX : (R && Cc && D && X && A) ? EPI_RCDXA
+                           : (R && Cc && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
+            const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
+            const float bias2 = (row_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
+            const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+                // residual loads of this warp's first output group go out before waiting for the accumulator
+                EpiLoads cur{}, nxt{};
+                auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
+                auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4; };
+                if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout);
                 mbar_wait_relaxed(accB_full, tl & 1u);
                 tc_fence_after();
                 for (int col = worker * 16; col < UN2; col += n_workers * 16) {
