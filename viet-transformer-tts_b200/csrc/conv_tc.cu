@@ -744,10 +744,8 @@ static int tc_prepare(TcLaunch &L, int fmt, const uint16_t *act, int B, int L_in
 // into accumulator B, which gets the usual fused epilogue (bias, residual, MRF sum/mean, 16-bit copy).
 // Saves the xt round trip through HBM (4 of the 16 bytes per element of a unit), one launch and one tile pass.
 // ---------------------------------------------------------------------------------------------
-constexpr int UNA = 160;           // conv1 positions per tile (UMMA N of phase A, one of two TMEM accumulators)
-constexpr int UN2 = 144;           // conv2 output positions per tile (UMMA N of phase B)
+constexpr int UN2 = 240;           // conv2 output positions per tile (UMMA N of phase B)
 constexpr int UXT_OFF = 8;         // xt row 0 is position i0 - 8 (covers conv2 half-widths up to 8)
-constexpr int U_TMEM_A1 = 160, U_TMEM_B = 320;   // TMEM column bases: A0 @0, A1 @160, B @320 (+144 = 464 <= 512)
 
 struct TcUnitParams {
     TcConvParams e;                // phase-B epilogue + shared geometry (taps/tap_off0/tap_step describe conv1)
@@ -757,10 +755,6 @@ struct TcUnitParams {
     int xt_chunks;                 // C / chunk channels
 };
 
-// Pipeline per CTA (one MMA-issuing warp, two epilogue groups):
-//   MMA:        A(0) | A(1) B(0) | A(2) B(1) | ...      A(t+1) goes to the other A accumulator, so the tensor pipe
-//   operand EA:        EA(0)     | EA(1)     | ...      works on conv1 of the next tile while the operand epilogue
-//   output  EB:             EB(0)      | EB(1) ...      turns the current one into conv2's shared-memory operand.
 template <int ROWB, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w1,
@@ -768,10 +762,9 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const TcConvParams &p = u.e;
     constexpr int CH = ROWB / 2;
     constexpr int KSTEPS = CH / 16;
-    constexpr int UACT_ROWS = 256;                // 160 + halo (<= 64) rounded up to 64-row boxes
-    constexpr int ACT_BYTES = UACT_ROWS * ROWB;
+    constexpr int ACT_BYTES = ACT_ROWS * ROWB;
     constexpr int W_BYTES = TM * ROWB;
-    constexpr int XT_BYTES = UNA * ROWB;          // one 64/32-channel chunk of the xt tile (160 rows = 20 swizzle atoms)
+    constexpr int XT_BYTES = TN * ROWB;          // one 64/32-channel chunk of the xt tile
     extern __shared__ __align__(1024) uint8_t smem[];
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("vtts: smem base not 1024-byte aligned\n"); __trap(); }
     const uint32_t ACT_STAGES = (uint32_t)p.act_stages, W_STAGES = (uint32_t)p.w_stages;
@@ -781,8 +774,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + (size_t)u.xt_chunks * XT_BYTES);
     uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
     uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
-    uint64_t *accA_full = w_empty + W_STAGES;     // [2]
-    uint64_t *xt_full = accA_full + 2, *xt_empty = xt_full + 1, *accB_full = xt_empty + 1, *accB_empty = accB_full + 1;
+    uint64_t *accA_full = w_empty + W_STAGES, *xt_full = accA_full + 1, *accB_full = xt_full + 1, *accB_empty = accB_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 1);
     int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
 
@@ -790,30 +782,21 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
-    const int nbox = (UNA + span + BOX_ROWS - 1) / BOX_ROWS;
+    const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
     const int h2 = (u.taps2 - 1) / 2;
     const int ncta = (int)gridDim.x;
-    const int n_grp = EPI_WARPS / 2;                      // warps per epilogue group (operand / output)
+    const int n_epi = EPI_WARPS / 2;                      // warps per epilogue group (operand / output)
 
-    // work items: (time tile of UN2 outputs, batch); m_blocks == 1.  Every role walks the same list of LIVE items.
+    // work items: (time tile of UN2 outputs, batch); m_blocks == 1
     auto tile_i0 = [&](int item, int &i0, int &b) { b = item / p.t_tiles; i0 = (item - b * p.t_tiles) * UN2; };
     const bool trimming = p.lens != nullptr;
-    auto next_live = [&](int item) -> int {               // first live item >= item in this CTA's stride, or total
-        for (; item < p.total_tiles; item += ncta) {
-            if (!trimming) break;
-            int i0, b;
-            tile_i0(item, i0, b);
-            if (i0 < s_lim[b]) break;
-        }
-        return item < p.total_tiles ? item : p.total_tiles;
-    };
+    auto tile_live = [&](int i0, int b) -> bool { return !trimming || i0 < s_lim[b]; };
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
         for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(&accA_full[0], 1); mbar_init(&accA_full[1], 1);
-        mbar_init(xt_full, (uint32_t)n_grp); mbar_init(xt_empty, 1);
-        mbar_init(accB_full, 1); mbar_init(accB_empty, (uint32_t)n_grp);
+        mbar_init(accA_full, 1); mbar_init(xt_full, (uint32_t)n_epi);
+        mbar_init(accB_full, 1); mbar_init(accB_empty, (uint32_t)n_epi);
         fence_barrier_init();
     }
     constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2;
@@ -830,13 +813,13 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int tps = p.tps;
 
     if (warp == WARP_ACT) {
-        // activation tiles are consumed by phase A only, in live-item order
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
             uint32_t s = 0, ph = 0;
-            for (int item = next_live(blockIdx.x); item < p.total_tiles; item = next_live(item + ncta)) {
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
                 for (int c = 0; c < p.chunks; ++c) {
                     mbar_wait(&act_empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
@@ -848,33 +831,31 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
         }
     } else if (warp == WARP_W) {
-        // weight tiles in the MMA issue order: W1(first), then per item: W1(next item), W2(this item)
         if (lane == 0) {
             tma_prefetch_desc(&tm_w1);
             tma_prefetch_desc(&tm_w2);
             uint32_t s = 0, ph = 0;
             const size_t stage_bytes = (size_t)W_BYTES * tps;
-            auto stream = [&](const CUtensorMap *tm, int ntaps) {
-                for (int c = 0; c < p.chunks; ++c)
-                    for (int j = 0; j < ntaps; j += tps) {
-                        mbar_wait(&w_empty[s], ph ^ 1u);
-                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));
-                        tma_load_3d(s_w + (size_t)s * stage_bytes, tm, &w_full[s], c * CH, 0, j);
-                        if (++s == W_STAGES) { s = 0; ph ^= 1u; }
-                    }
-            };
-            int item = next_live(blockIdx.x);
-            if (item < p.total_tiles) stream(&tm_w1, p.taps);
-            while (item < p.total_tiles) {
-                const int nxt = next_live(item + ncta);
-                if (nxt < p.total_tiles) stream(&tm_w1, p.taps);
-                stream(&tm_w2, u.taps2);
-                item = nxt;
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+                for (int phase = 0; phase < 2; ++phase) {
+                    const CUtensorMap *tm = phase == 0 ? &tm_w1 : &tm_w2;
+                    const int ntaps = phase == 0 ? p.taps : u.taps2;
+                    for (int c = 0; c < p.chunks; ++c)
+                        for (int j = 0; j < ntaps; j += tps) {
+                            mbar_wait(&w_empty[s], ph ^ 1u);
+                            mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));
+                            tma_load_3d(s_w + (size_t)s * stage_bytes, tm, &w_full[s], c * CH, 0, j);
+                            if (++s == W_STAGES) { s = 0; ph ^= 1u; }
+                        }
+                }
             }
         }
     } else if (warp == WARP_MMA) {
         // whole warp converged; elect.sync inside the step picks the issuing lane
-        constexpr uint32_t idescA = make_idesc_16(TM, UNA, FMT), idescB = make_idesc_16(TM, UN2, FMT);
+        constexpr uint32_t idescA = make_idesc_16(TM, TN, FMT), idescB = make_idesc_16(TM, UN2, FMT);
         const uint32_t wfull0 = smem_u32(w_full), wempty0 = smem_u32(w_empty);
         const uint64_t adesc_first = make_smem_desc(smem_u32(s_w), ROWB, 0);
         const uint64_t bdesc_first = make_smem_desc(smem_u32(s_act), ROWB, 0);
@@ -886,7 +867,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const long long tap_step = (long long)p.tap_step * (ROWB >> 4);
         const uint64_t xtap0 = (uint64_t)((UXT_OFF - h2) * (ROWB >> 4));   // conv2 tap 0 row, 16-byte units
         constexpr uint64_t XTAP_STEP = (uint64_t)(ROWB >> 4);
-        uint32_t sa = 0, aph = 0, sw = 0, wph = 0;
+        uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;
         uint64_t adesc = adesc_first, bstage = bdesc_first;
         uint32_t w_ready = 0;
         auto step = [&](uint32_t tmem_d, uint64_t bdesc, uint64_t bdesc1, uint32_t idesc, uint32_t acc) {
@@ -905,17 +886,21 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             sw = sn; wph = pn;
             if (sn == 0) adesc = adesc_first;
         };
-        // phase A of the tl-th live tile -> A accumulator (tl & 1).  That accumulator is free: xt_full of tile tl-2 was
-        // observed before its phase B was issued, i.e. the operand epilogue had finished reading it.
-        auto phase_a = [&](uint32_t tl) {
-            const uint32_t tmem_d = tmem_base + ((tl & 1u) ? U_TMEM_A1 : 0);
+        for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+            {
+                int i0, b;
+                tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
+            }
+            // ---- phase A: conv1 -> accumulator A (columns 0..255).  A is free: xt_full of the previous tile was
+            // observed before its phase B was issued, i.e. every epilogue warp had finished reading A.
             uint32_t acc = 0;
             for (int c = 0; c < p.chunks; ++c) {
                 mbar_wait(&act_full[sa], aph);
                 uint64_t bdesc = bstage + (uint64_t)tap0;
                 for (int j = 0; j < p.taps; j += tps) {
                     const uint64_t bdesc1 = (j + 1 < p.taps) ? bdesc + (uint64_t)tap_step : bdesc;
-                    step(tmem_d, bdesc, bdesc1, idescA, acc);
+                    step(tmem_base, bdesc, bdesc1, idescA, acc);
                     acc = 1;
                     bdesc += (uint64_t)(tap_step * tps);
                 }
@@ -923,38 +908,29 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 bstage += B_STAGE_STEP;
                 if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; bstage = bdesc_first; }
             }
-            umma_commit_elect(&accA_full[tl & 1u]);
-        };
-        uint32_t tl = 0;
-        int item = next_live(blockIdx.x);
-        if (item < p.total_tiles) phase_a(0);
-        while (item < p.total_tiles) {
-            const int nxt = next_live(item + ncta);
-            if (nxt < p.total_tiles) phase_a(tl + 1);         // conv1 of the next tile runs while EA converts this one
-            // ---- phase B: conv2 on the xt tile -> accumulator B
-            mbar_wait(xt_full, tl & 1u);                      // operand epilogue wrote the xt tile
+            umma_commit_elect(accA_full);
+            // ---- phase B: conv2 on the xt tile -> accumulator B (columns 256..495)
+            mbar_wait(xt_full, tl & 1u);                      // epilogue wrote the operand tile (and drained A)
             mbar_wait(accB_empty, (tl & 1u) ^ 1u);            // previous tile's output epilogue drained B
             tc_fence_after();
-            uint32_t acc = 0;
+            acc = 0;
             uint64_t xchunk = xdesc_first;
             for (int c = 0; c < p.chunks; ++c) {
                 uint64_t xdesc = xchunk + xtap0;
                 for (int j = 0; j < u.taps2; j += tps) {
                     const uint64_t xdesc1 = (j + 1 < u.taps2) ? xdesc + XTAP_STEP : xdesc;
-                    step(tmem_base + U_TMEM_B, xdesc, xdesc1, idescB, acc);
+                    step(tmem_base + TN, xdesc, xdesc1, idescB, acc);
                     acc = 1;
                     xdesc += XTAP_STEP * (uint64_t)tps;
                 }
                 xchunk += X_CHUNK_STEP;
             }
-            umma_commit_elect(xt_empty);                      // xt tile may be overwritten once these MMAs retire
             umma_commit_elect(accB_full);
             ++tl;
-            item = nxt;
         }
     } else {
-        // ===== epilogue warps: operand group (accumulator A -> xt tile in shared memory, warps 0-7) and output group
-        // (accumulator B -> HBM, warps 8-15) run concurrently on different tiles =====
+        // ===== epilogue warps: two groups so that the operand epilogue of tile t+1 (accumulator A -> xt tile in
+        // shared memory, warps 0-7) overlaps the output epilogue of tile t (accumulator B -> HBM, warps 8-15) =====
         const int ew = warp, quarter = warp & 3;
         const bool is_ea = ew < EPI_WARPS / 2;
         constexpr int SHARERS = EPI_WARPS / 2 / 4;                   // warps per lane quarter within a group (2)
@@ -967,19 +943,19 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         uint32_t tl = 0;
         if (is_ea) {
             const float bias1 = (row_ok && u.bias1) ? __ldg(u.bias1 + ch) : 0.f;
+            // swizzled xt address pieces of this thread's channel
             const int kc = ch % CH;
             uint8_t *xt_ch = s_xt + (size_t)(ch / CH) * XT_BYTES + (kc & 7) * 2;
             const int kchunk = kc >> 3;
-            for (int item = next_live(blockIdx.x); item < p.total_tiles; item = next_live(item + ncta), ++tl) {
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
-                mbar_wait_relaxed(&accA_full[tl & 1u], (tl >> 1) & 1u);
-                mbar_wait_relaxed(xt_empty, (tl & 1u) ^ 1u);   // conv2 of the previous tile finished reading the xt tile
+                if (!tile_live(i0, b)) continue;
+                mbar_wait_relaxed(accA_full, tl & 1u);
                 tc_fence_after();
-                const uint32_t acol = (tl & 1u) ? U_TMEM_A1 : 0;
-                for (int col = worker * 16; col < UNA; col += n_workers * 16) {
+                for (int col = worker * 16; col < TN; col += n_workers * 16) {
                     uint32_t v[16];
-                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acol + (uint32_t)col, v);
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
                     tmem_ld_wait();
                     if (row_ok) {
 #pragma unroll
@@ -997,6 +973,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(xt_full);
+                ++tl;
             }
         } else {
             const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
@@ -1007,9 +984,10 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
             const float bias2 = (row_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
             const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
-            for (int item = next_live(blockIdx.x); item < p.total_tiles; item = next_live(item + ncta), ++tl) {
+            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
+                if (!tile_live(i0, b)) continue;
                 // residual loads of this warp's first output group go out before waiting for the accumulator
                 EpiLoads cur{}, nxt{};
                 auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
@@ -1021,7 +999,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     const int ibase = i0 + col;
                     if (ibase >= p.n_pos) break;
                     uint32_t v[16];
-                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(U_TMEM_B + col), v);
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(TN + col), v);
                     cur = nxt;
                     const bool fast = group_fast(ibase);
                     const int col_n = col + n_workers * 16;
@@ -1038,6 +1016,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(accB_empty);
+                ++tl;
             }
         }
     }
@@ -1102,13 +1081,12 @@ static int unit_prepare(TcUnitLaunch &L, int fmt, const uint16_t *act, int B, in
     p.batch = B;
     if (p.lens && B > MAX_TRIM_BATCH) p.lens = nullptr;
     p.tps = p.chunks == 1 ? 2 : 1;
-    // shared memory: activation stages of 256 rows, weight stages of tps x 128 rows, the xt tile (160 rows per chunk)
-    if (rowb == 64) { p.act_stages = 4; p.w_stages = 4; }          // 64 + 64 + 10 KB
-    else if (p.chunks == 1) { p.act_stages = 3; p.w_stages = 3; }  // 96 + 96 + 20 KB
-    else { p.act_stages = 3; p.w_stages = 5; }                     // 96 + 80 + 40 KB
+    if (rowb == 64) { p.act_stages = 4; p.w_stages = 4; }          // 80 + 64 + 16 KB
+    else if (p.chunks == 1) { p.act_stages = 2; p.w_stages = 3; }  // 80 + 96 + 32 KB
+    else { p.act_stages = 2; p.w_stages = 4; }                     // 80 + 64 + 64 KB
     L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.xt_chunks = p.chunks;
-    L.smem = (size_t)p.act_stages * 256 * rowb + (size_t)p.w_stages * p.tps * TM * rowb + (size_t)p.chunks * UNA * rowb +
-             (size_t)(2 * p.act_stages + 2 * p.w_stages + 6) * 8 + 16 + MAX_TRIM_BATCH * sizeof(int);
+    L.smem = (size_t)p.act_stages * ACT_ROWS * rowb + (size_t)p.w_stages * p.tps * TM * rowb + (size_t)p.chunks * TN * rowb +
+             (size_t)(2 * p.act_stages + 2 * p.w_stages + 4) * 8 + 16 + MAX_TRIM_BATCH * sizeof(int);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc unit: %zu B shared memory", L.smem);
     const int sms = tc_num_sms();
     L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
