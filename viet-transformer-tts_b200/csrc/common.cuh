@@ -88,6 +88,17 @@ __device__ __forceinline__ uint16_t cvt16(float v, int fmt) {
     v = fminf(fmaxf(v, -65504.f), 65504.f);  // saturate instead of overflowing to inf
     return __half_as_ushort(__float2half_rn(v));
 }
+// two values -> one 32-bit register, `lo` in the low half (same rounding/saturation as cvt16)
+__device__ __forceinline__ uint32_t cvt16x2(float lo, float hi, int fmt) {
+    if (fmt == VTTS_FMT_BF16) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<const uint32_t *>(&v);
+    }
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    const __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
 __device__ __forceinline__ float cvt16_to_f32(uint16_t u, int fmt) {
     return fmt == VTTS_FMT_BF16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
 }

@@ -85,6 +85,7 @@ constexpr int PRODUCER_WARPS = 2 + W_PRODUCERS;  // activation producer, weight 
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter
 constexpr int MAX_TRIM_BATCH = 256; // padding trim keeps per-batch limits in shared memory
 
+static int g_trace_on = 0;   // vtts_dbg_trace: 1 = debug conv entry, 100 + n = n-th launch of the next forward
 // debug trace (vtts_dbg_trace_*): 16 stamps per tile for the first TRACE_TILES tiles of block 0
 constexpr int TRACE_TILES = 64;
 __device__ long long g_trace[TRACE_TILES * 16];
@@ -172,13 +173,17 @@ __device__ __forceinline__ void epi_group16(const uint32_t (&v)[16], float bias,
     using F = EpiFlags<MODE>;
     const int C = C_CT ? C_CT : p.cout;
     const int lda = C_CT ? C_CT : p.out_a_ld;
+    // the running sum is read and rewritten in place: issue all four loads before the first store, otherwise every
+    // load waits behind the previous stores (possible aliasing) and exposes its full latency
+    float4 accv[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        accv[m] = F::ACC ? *reinterpret_cast<const float4 *>(px + (size_t)m * C * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         float val[4];
         const float rr[4] = {res.r[m].x, res.r[m].y, res.r[m].z, res.r[m].w};
-        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (F::ACC) acc4 = *reinterpret_cast<const float4 *>(px + (size_t)m * C * 4);
-        const float aa[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+        const float aa[4] = {accv[m].x, accv[m].y, accv[m].z, accv[m].w};
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             float x = __uint_as_float(v[m * 4 + d]) + bias;
@@ -894,6 +899,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
             // ---- phase A: conv1 -> accumulator A (columns 0..255).  A is free: xt_full of the previous tile was
             // observed before its phase B was issued, i.e. every epilogue warp had finished reading A.
+            if (lane == 0) VTTS_TRACE(0);
             uint32_t acc = 0;
             for (int c = 0; c < p.chunks; ++c) {
                 mbar_wait(&act_full[sa], aph);
@@ -909,9 +915,12 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; bstage = bdesc_first; }
             }
             umma_commit_elect(accA_full);
+            if (lane == 0) VTTS_TRACE(1);
             // ---- phase B: conv2 on the xt tile -> accumulator B (columns 256..495)
             mbar_wait(xt_full, tl & 1u);                      // epilogue wrote the operand tile (and drained A)
+            if (lane == 0) VTTS_TRACE(2);
             mbar_wait(accB_empty, (tl & 1u) ^ 1u);            // previous tile's output epilogue drained B
+            if (lane == 0) VTTS_TRACE(3);
             tc_fence_after();
             acc = 0;
             uint64_t xchunk = xdesc_first;
@@ -926,6 +935,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 xchunk += X_CHUNK_STEP;
             }
             umma_commit_elect(accB_full);
+            if (lane == 0) VTTS_TRACE(4);
             ++tl;
         }
     } else {
@@ -942,37 +952,63 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const bool rows_full = (quarter % qpc) * 32 + 32 <= p.n_total;
         uint32_t tl = 0;
         if (is_ea) {
-            const float bias1 = (row_ok && u.bias1) ? __ldg(u.bias1 + ch) : 0.f;
-            // swizzled xt address pieces of this thread's channel
-            const int kc = ch % CH;
-            uint8_t *xt_ch = s_xt + (size_t)(ch / CH) * XT_BYTES + (kc & 7) * 2;
-            const int kchunk = kc >> 3;
+            // Accumulator A -> LeakyReLU'd 16-bit xt tile.  mma-style fragments (tcgen05.ld 16x256b: a thread holds two
+            // consecutive positions of one channel) are packed in pairs and stored transposed with stmatrix, so one
+            // instruction writes 8 positions x 32 channels as swizzled 16-byte chunks: the K-major rows conv2 reads.
+            const int chbase = (quarter % qpc) * 32;                 // first channel of this warp's 32 TMEM lanes
+            const int fr = lane >> 2, fc = (lane & 3) * 2;           // fragment row (channel) / first column (position)
+            float b1[4];                                             // conv1 bias of channels chbase + 16*L + 8*h + fr
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b1[q] = u.bias1 ? __ldg(u.bias1 + chbase + (q >> 1) * 16 + (q & 1) * 8 + fr) : 0.f;
+            const uint32_t xt_row0 = smem_u32(s_xt) + (uint32_t)(chbase / CH) * XT_BYTES;
+            const uint32_t cblk = (uint32_t)((chbase % CH) / 8 + (lane >> 3));   // 16-byte chunk of matrix lane/8
+            const int mrow = lane & 7;                               // row of that matrix this thread addresses
+            const uint32_t t_lo = tmem_base + ((uint32_t)(quarter * 32) << 16), t_hi = t_lo + (16u << 16);
             for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
                 mbar_wait_relaxed(accA_full, tl & 1u);
+                if (ew == 0 && lane == 0) VTTS_TRACE(5);
                 tc_fence_after();
-                for (int col = worker * 16; col < TN; col += n_workers * 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
+                const int pos0 = i0 - UXT_OFF;
+                const bool interior = pos0 >= 0 && pos0 + TN <= p.n_pos;      // no conv2 zero padding inside this tile
+                uint32_t lo[8], hi[8];
+                int col = worker * 16;
+                if (col < TN) { tmem_ld_16x256_x2(t_lo + (uint32_t)col, lo); tmem_ld_16x256_x2(t_hi + (uint32_t)col, hi); }
+                for (; col < TN; col += n_workers * 16) {
                     tmem_ld_wait();
-                    if (row_ok) {
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        // e: bit 2 = columns +8, bit 1 = lanes +8, bit 0 = column +1
+                        v[e] = lrelu_max(__uint_as_float(lo[e]) + b1[(e >> 1) & 1], u.slope_mid);
+                        v[8 + e] = lrelu_max(__uint_as_float(hi[e]) + b1[2 + ((e >> 1) & 1)], u.slope_mid);
+                    }
+                    const int col_n = col + n_workers * 16;
+                    if (col_n < TN) { tmem_ld_16x256_x2(t_lo + (uint32_t)col_n, lo); tmem_ld_16x256_x2(t_hi + (uint32_t)col_n, hi); }
+                    if (!interior) {                                  // conv2 zero-pads its own input
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const int r = col + e;
-                            const int pos = i0 - UXT_OFF + r;
-                            float val = lrelu_max(__uint_as_float(v[e]) + bias1, u.slope_mid);
-                            if (pos < 0 || pos >= p.n_pos) val = 0.f;      // conv2 zero-pads its own input
-                            const int swz = ROWB == 128 ? (r & 7) : ((r >> 1) & 3);
-                            *reinterpret_cast<uint16_t *>(xt_ch + (size_t)r * ROWB + ((kchunk ^ swz) << 4)) = cvt16(val, FMT);
+                            const int pos = pos0 + col + ((e >> 2) & 1) * 8 + fc + (e & 1);
+                            if (pos < 0 || pos >= p.n_pos) v[e] = 0.f;
                         }
+                    }
+#pragma unroll
+                    for (int s8 = 0; s8 < 2; ++s8) {                  // positions col + 8*s8 .. +7
+                        const int r = col + s8 * 8 + mrow;
+                        const uint32_t swz = ROWB == 128 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+                        const uint32_t addr = xt_row0 + (uint32_t)r * ROWB + ((cblk ^ swz) << 4);
+                        const int o = s8 * 4;
+                        stmatrix_x4_trans(addr, cvt16x2(v[o], v[o + 1], FMT), cvt16x2(v[o + 2], v[o + 3], FMT),
+                                          cvt16x2(v[8 + o], v[8 + o + 1], FMT), cvt16x2(v[8 + o + 2], v[8 + o + 3], FMT));
                     }
                 }
                 fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor-core (async) proxy
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(xt_full);
+                if (ew == 0 && lane == 0) VTTS_TRACE(6);
                 ++tl;
             }
         } else {
@@ -988,12 +1024,28 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
+                {   // L2 prefetch of the fp32 streams the next live tile reads (residual, running MRF sum): in the
+                    // time-packed layout a tile's rows are one contiguous block of (positions / 4) * C * 16 bytes
+                    int nx = item + ncta, i0n = 0, bn = 0;
+                    for (; nx < p.total_tiles; nx += ncta) { tile_i0(nx, i0n, bn); if (tile_live(i0n, bn)) break; }
+                    if (nx < p.total_tiles && (R || Cc)) {
+                        const int rows4 = min(UN2 / 4, p.L4 - i0n / 4);
+                        const long long off = ((long long)bn * p.L4 + i0n / 4) * p.cout * 4;
+                        const int n_lines = rows4 * p.cout / 8;                 // 128-byte lines
+                        for (int l = threadIdx.x - (EPI_WARPS / 2) * 32; l < n_lines; l += (EPI_WARPS / 2) * 32) {
+                            if (R) prefetch_l2(p.res + off + (long long)l * 32);
+                            if (Cc) prefetch_l2(p.out_x + off + (long long)l * 32);
+                        }
+                    }
+                }
                 // residual loads of this warp's first output group go out before waiting for the accumulator
                 EpiLoads cur{}, nxt{};
                 auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
                 auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4; };
                 if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout);
+                if (ew == EPI_WARPS / 2 && lane == 0) VTTS_TRACE(7);
                 mbar_wait_relaxed(accB_full, tl & 1u);
+                if (ew == EPI_WARPS / 2 && lane == 0) VTTS_TRACE(8);
                 tc_fence_after();
                 for (int col = worker * 16; col < UN2; col += n_workers * 16) {
                     const int ibase = i0 + col;
@@ -1016,6 +1068,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(accB_empty);
+                if (ew == EPI_WARPS / 2 && lane == 0) VTTS_TRACE(9);
                 ++tl;
             }
         }
@@ -1417,6 +1470,7 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
         pr.B = B; pr.L = Lpos;
         cudaEventRecord(pr.a, st);
     }
+    if (g_trace_on >= 100 && h->launch_count == g_trace_on - 100) L.u.e.trace = 1;   // debug: trace this launch of the forward
     if ((rc = unit_launch(L, st))) return rc;
     if (prof_enabled()) { cudaEventRecord(pr.b, st); g_prof.push_back(pr); }
     h->launch_count++;
@@ -1731,7 +1785,6 @@ extern "C" int vtts_dbg_umma_bench(int N, int rowb, int row_shift, int reps, int
     return VTTS_OK;
 }
 
-static int g_trace_on = 0;
 extern "C" int vtts_dbg_trace(int enable, long long *host_out, int n) {
     g_trace_on = enable;
     if (host_out && n > 0) {

@@ -371,6 +371,25 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 
+// 16 lanes x 256 bits x2: the mma-style accumulator fragment.  Thread T of the warp gets, for the 16 TMEM lanes
+// starting at taddr's lane and the 16 columns starting at its column:
+//   r[0], r[1] = lane T/4,     columns 2*(T%4), 2*(T%4)+1        r[4..7]: the same for columns +8
+//   r[2], r[3] = lane T/4 + 8, columns 2*(T%4), 2*(T%4)+1
+__device__ __forceinline__ void tmem_ld_16x256_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// Four 8x8 16-bit matrices, stored transposed: thread T passes the shared-memory address of row T%8 of matrix T/8
+// (16 bytes per row); register i is the thread's fragment of matrix i (element pair (T/4, 2*(T%4)), (T/4, 2*(T%4)+1)),
+// which lands in rows 2*(T%4), 2*(T%4)+1 at 16-bit column T/4.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b),
+                 "r"(c), "r"(d)
+                 : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // Instruction descriptor, kind::f16: 16-bit x 16-bit -> fp32, both operands K-major.
 // fmt: 0 = bf16 operands, 1 = fp16 operands (same tensor-core rate; fp16 has 3 more mantissa bits).
