@@ -32,6 +32,9 @@ with torch.no_grad():
         for i in range(2, 10):
             r = t[i] - t0
             print(f"{i:4d} | {r[0]:9d} {r[1]:9d} {r[2]:8d} {r[3]:8d} {r[4]:9d} | {r[5]:8d} {r[6]:8d} | {r[7]:8d} {r[8]:8d} {r[9]:8d}")
+        if t[3, 10] != 0:
+            e = t[3:12]
+            print(f"  conv1 issuer: waits {np.mean(e[:,10]-e[:,0]):.0f}  mma issue {np.mean(e[:,11]-e[:,10]):.0f}  commits {np.mean(e[:,1]-e[:,11]):.0f}  A period {np.diff(e[:,0]).mean():.0f} | conv2 issuer: B period {np.diff(e[:,4]).mean():.0f}")
         e = t[3:12]
         print(f"period {np.diff(e[:,0]).mean():.0f} | A issue {np.mean(e[:,1]-e[:,0]):.0f}  wait xt {np.mean(e[:,2]-e[:,1]):.0f}  wait Bempty {np.mean(e[:,3]-e[:,2]):.0f}"
               f"  B issue {np.mean(e[:,4]-e[:,3]):.0f} | EA: accA_full after A-issued {np.mean(e[:,5]-e[:,1]):.0f}  EA busy {np.mean(e[:,6]-e[:,5]):.0f}"

@@ -89,7 +89,7 @@ static int g_trace_on = 0;   // vtts_dbg_trace: 1 = debug conv entry, 100 + n = 
 // debug trace (vtts_dbg_trace_*): 16 stamps per tile for the first TRACE_TILES tiles of block 0
 constexpr int TRACE_TILES = 64;
 __device__ long long g_trace[TRACE_TILES * 16];
-#define VTTS_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && tl < TRACE_TILES) g_trace[tl * 16 + (slot)] = clock64(); } while (0)
+#define VTTS_TRACE(slot) do { if ((p.trace & 1) && blockIdx.x == 0 && tl < TRACE_TILES) g_trace[tl * 16 + (slot)] = clock64(); } while (0)
 constexpr int TC_THREADS = (PRODUCER_WARPS + EPI_WARPS) * 32;
 
 struct TcConvParams {
@@ -1166,6 +1166,548 @@ static int unit_launch(const TcUnitLaunch &L, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Narrow fused unit (C = 32 or 64): the same conv1 -> LeakyReLU -> conv2 (+ residual epilogue) as unit_tc_kernel, laid
+// out for layers whose 64 (or 32, replicated twice) output channels fill only half of a 128-row MMA:
+//   * M = 64 MMAs (same cycles as M = 128, half the weight bytes); accumulator row r lives in TMEM lane 32*(r/16)+r%16,
+//     so every warp quarter owns 16 channels and both epilogues work on 16-lane mma-style fragments;
+//   * the weights of both convs stay resident in shared memory for the whole kernel (only conv1 taps that do not fit
+//     are streamed through a small ring) - no per-tile weight traffic, so small tiles cost nothing extra;
+//   * four accumulators of 128 columns (A0, A1, B0, B1): conv1 of tile t+1 is issued before conv2 of tile t, so the
+//     tensor pipe keeps running while the operand epilogue builds the xt tile, and the output epilogue of tile t has
+//     until conv2 of tile t+2 to drain.
+// ---------------------------------------------------------------------------------------------
+constexpr int VN_A = 128;          // conv1 positions per tile (UMMA N of phase A)
+constexpr int VN_B = 112;          // conv2 output positions per tile (UMMA N of phase B)
+constexpr int V_XT_OFF = 8;        // xt row 0 is position i0 - 8
+constexpr int V_ACT_ROWS = 192;    // VN_A + dilation halo (<= 64)
+constexpr int V_M = 64;            // accumulator rows
+constexpr int V_THREADS = (EPI_WARPS + 4) * 32;   // 16 epilogue warps, activation + weight producers, two MMA issuers
+
+struct TcUnit64Params {
+    TcConvParams e;                // phase-B epilogue + shared geometry (taps/tap_off0/tap_step describe conv1)
+    const float *bias1;
+    float slope_mid;
+    int taps2;
+    int n_stream;                  // conv1 taps [0, n_stream) go through the ring, everything else is resident
+    int n_res;                     // resident taps: conv1 [n_stream, taps) then conv2 [0, taps2)
+};
+
+struct EpiLoads2 { float4 r[2]; };
+
+// two float4 (4 consecutive positions each, 8 positions apart) of one channel
+template <int FMT, int C_CT, int MODE>
+__device__ __forceinline__ void epi64_pair(const float (&q)[8], float bias, const TcConvParams &p, const EpiLoads2 &res,
+                                           float *px, uint16_t *pa) {
+    using F = EpiFlags<MODE>;
+    const int C = C_CT ? C_CT : p.cout;
+    const int lda = C_CT ? C_CT : p.out_a_ld;
+    float4 accv[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+        accv[m] = F::ACC ? *reinterpret_cast<const float4 *>(px + (size_t)m * 2 * C * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        float val[4];
+        const float rr[4] = {res.r[m].x, res.r[m].y, res.r[m].z, res.r[m].w};
+        const float aa[4] = {accv[m].x, accv[m].y, accv[m].z, accv[m].w};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            float x = q[m * 4 + d] + bias;
+            if (F::RES) x = x + rr[d];
+            if (F::ACC) x = aa[d] + x;
+            if (F::DIV) x = x * p.inv_div;
+            val[d] = x;
+        }
+        if (F::X) *reinterpret_cast<float4 *>(px + (size_t)m * 2 * C * 4) = make_float4(val[0], val[1], val[2], val[3]);
+        if (F::A) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) pa[(size_t)(m * 8 + d) * lda] = cvt16(lrelu_max(val[d], p.slope_out), FMT);
+        }
+    }
+}
+template <int FMT, int MODE>
+__device__ __forceinline__ void epi64_pair_c(int c_ct, const float (&q)[8], float bias, const TcConvParams &p,
+                                             const EpiLoads2 &res, float *px, uint16_t *pa) {
+    switch (c_ct) {
+        case 32: epi64_pair<FMT, 32, MODE>(q, bias, p, res, px, pa); return;
+        case 64: epi64_pair<FMT, 64, MODE>(q, bias, p, res, px, pa); return;
+        default: epi64_pair<FMT, 0, MODE>(q, bias, p, res, px, pa); return;
+    }
+}
+template <int FMT>
+__device__ __forceinline__ void epi64_pair_dispatch(int mode, int c_ct, const float (&q)[8], float bias, const TcConvParams &p,
+                                                    const EpiLoads2 &res, float *px, uint16_t *pa) {
+    switch (mode) {
+        case EPI_RXA: epi64_pair_c<FMT, EPI_RXA>(c_ct, q, bias, p, res, px, pa); return;
+        case EPI_RX: epi64_pair_c<FMT, EPI_RX>(c_ct, q, bias, p, res, px, pa); return;
+        case EPI_RCX: epi64_pair_c<FMT, EPI_RCX>(c_ct, q, bias, p, res, px, pa); return;
+        case EPI_RCDXA: epi64_pair_c<FMT, EPI_RCDXA>(c_ct, q, bias, p, res, px, pa); return;
+        default: epi64_pair_c<FMT, EPI_RCDX>(c_ct, q, bias, p, res, px, pa); return;
+    }
+}
+// per-element path (tile edges, unusual epilogue combinations)
+template <int FMT>
+__device__ __forceinline__ void epi64_pair_edge(const float (&q)[8], float bias, const TcConvParams &p, int b, int pos0, int ch) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int t = pos0 + (e >> 2) * 8 + (e & 3);
+        if (t < p.n_pos && t < p.L_out) {
+            const long long xo = tp4_off(b, p.L4, t, p.cout, ch);
+            float val = q[e] + bias;
+            if (p.res) val = val + __ldg(p.res + xo);
+            if (p.accumulate) val = p.out_x[xo] + val;
+            if (p.divide_by > 0.f) val = val * p.inv_div;
+            if (p.out_x) p.out_x[xo] = val;
+            if (p.out_a) p.out_a[((long long)b * p.L_out + t) * p.out_a_ld + ch] = cvt16(lrelu_max(val, p.slope_out), FMT);
+        }
+    }
+}
+
+template <int ROWB, int FMT>
+__global__ void __launch_bounds__(V_THREADS, 1)
+unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w1,
+                 const __grid_constant__ CUtensorMap tm_w2, const TcUnit64Params u) {
+    const TcConvParams &p = u.e;
+    constexpr int CH = ROWB / 2;                  // channels per operand row == C (one K chunk)
+    constexpr int KSTEPS = CH / 16;
+    constexpr int ACT_BYTES = V_ACT_ROWS * ROWB;
+    constexpr int TAPB = V_M * ROWB;              // one tap of weights: 64 rows
+    constexpr int XT_BYTES = VN_A * ROWB;
+    constexpr uint32_t COL_A1 = 128, COL_B0 = 256, COL_B1 = 384;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("vtts: smem base not 1024-byte aligned\n"); __trap(); }
+    const uint32_t ACT_STAGES = (uint32_t)p.act_stages, W_STAGES = (uint32_t)p.w_stages;
+    uint8_t *s_act = smem;
+    uint8_t *s_wres = s_act + (size_t)ACT_STAGES * ACT_BYTES;
+    uint8_t *s_wring = s_wres + (size_t)u.n_res * TAPB;
+    uint8_t *s_xt = s_wring + (size_t)W_STAGES * TAPB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + XT_BYTES);
+    uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
+    uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
+    uint64_t *wres_full = w_empty + W_STAGES;
+    uint64_t *accA_full = wres_full + 1;          // [2]
+    uint64_t *accA_empty = accA_full + 2;         // [2]
+    uint64_t *xt_full = accA_empty + 2, *xt_empty = xt_full + 1;
+    uint64_t *accB_full = xt_empty + 1;           // [2]
+    uint64_t *accB_empty = accB_full + 2;         // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 2);
+    int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
+    const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
+    const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
+    const int nbox = (VN_A + span + BOX_ROWS - 1) / BOX_ROWS;
+    const int ncta = (int)gridDim.x;
+    constexpr int N_GRP = EPI_WARPS / 2;          // warps per epilogue group
+
+    // work items: (time tile of VN_B outputs, batch).  Every role walks the same list of LIVE items (tiles that start
+    // before the utterance's trim limit); the walk is incremental - no division on the MMA issuers' path.
+    const bool trimming = p.lens != nullptr;
+    struct Walk { int item, t, b; };
+    auto walk_fix = [&](Walk &w) {                // normalise (t, b) and skip dead tiles
+        for (;;) {
+            if (w.t >= p.t_tiles) {
+                if (p.t_tiles >= ncta) { w.t -= p.t_tiles; ++w.b; }
+                else { w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; }
+            }
+            if (w.item >= p.total_tiles || !trimming || w.t * VN_B < s_lim[w.b]) return;
+            w.item += ncta; w.t += ncta;
+        }
+    };
+    auto walk_begin = [&]() { Walk w; w.item = (int)blockIdx.x; w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; walk_fix(w); return w; };
+    auto walk_next = [&](Walk &w) { w.item += ncta; w.t += ncta; walk_fix(w); };
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
+        for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        mbar_init(wres_full, 1);
+        mbar_init(&accA_full[0], 1); mbar_init(&accA_full[1], 1);
+        mbar_init(&accA_empty[0], N_GRP); mbar_init(&accA_empty[1], N_GRP);
+        mbar_init(xt_full, N_GRP); mbar_init(xt_empty, 1);
+        mbar_init(&accB_full[0], 1); mbar_init(&accB_full[1], 1);
+        mbar_init(&accB_empty[0], N_GRP); mbar_init(&accB_empty[1], N_GRP);
+        fence_barrier_init();
+    }
+    constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2, WARP_MMA_B = EPI_WARPS + 3;
+    if (warp == WARP_MMA) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (p.lens != nullptr)
+        for (int i = threadIdx.x; i < p.batch; i += blockDim.x) {
+            const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate + p.len_extra;
+            s_lim[i] = lim > 0x7fffffffLL ? 0x7fffffff : (int)lim;
+        }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == WARP_ACT) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_act);
+            uint32_t s = 0, ph = 0;
+            for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w)) {
+                const int i0 = w.t * VN_B, b = w.b;
+                mbar_wait(&act_empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
+                for (int bx = 0; bx < nbox; ++bx)
+                    tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s], 0,
+                                i0 - V_XT_OFF + min_off + bx * BOX_ROWS, b);
+                if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == WARP_W) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_w1);
+            tma_prefetch_desc(&tm_w2);
+            // resident weights, loaded once: conv1 taps [n_stream, taps), then all conv2 taps
+            mbar_arrive_expect_tx(wres_full, (uint32_t)(u.n_res * TAPB));
+            int slot = 0;
+            for (int j = u.n_stream; j < p.taps; ++j, ++slot) tma_load_3d(s_wres + (size_t)slot * TAPB, &tm_w1, wres_full, 0, 0, j);
+            for (int j = 0; j < u.taps2; ++j, ++slot) tma_load_3d(s_wres + (size_t)slot * TAPB, &tm_w2, wres_full, 0, 0, j);
+            if (u.n_stream > 0) {
+                uint32_t s = 0, ph = 0;
+                for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w))
+                    for (int j = 0; j < u.n_stream; ++j) {
+                        mbar_wait(&w_empty[s], ph ^ 1u);
+                        mbar_arrive_expect_tx(&w_full[s], (uint32_t)TAPB);
+                        tma_load_3d(s_wring + (size_t)s * TAPB, &tm_w1, &w_full[s], 0, 0, j);
+                        if (++s == W_STAGES) { s = 0; ph ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == WARP_MMA || warp == WARP_MMA_B) {
+        // Two MMA issuers share the tensor pipe: one issues conv1 of every tile, the other conv2.  With 64-cycle MMAs
+        // the per-tile barrier probes, commits and tile bookkeeping of a single issuer (well over 1000 cycles) would
+        // starve the pipe; split like this, one issuer's overhead hides behind the other's MMAs.
+        if (lane == 0) {
+            constexpr uint32_t idescA = make_idesc_16(V_M, VN_A, FMT), idescB = make_idesc_16(V_M, VN_B, FMT);
+            constexpr uint64_t ROW16 = (uint64_t)(ROWB >> 4);                // one operand row, in 16-byte units
+            constexpr uint64_t TAP16 = (uint64_t)(TAPB >> 4), ACT16 = (uint64_t)(ACT_BYTES >> 4);
+            const uint64_t wres_desc = make_smem_desc(smem_u32(s_wres), ROWB, 0);
+            mbar_wait(wres_full, 0);
+            tc_fence_after();
+            if (warp == WARP_MMA) {
+                const uint64_t wring_desc = make_smem_desc(smem_u32(s_wring), ROWB, 0);
+                const uint64_t act_desc = make_smem_desc(smem_u32(s_act), ROWB, 0);
+                const long long tap0 = (long long)(p.tap_off0 - min_off) * (long long)ROW16;
+                const uint64_t tap_step = (uint64_t)((long long)p.tap_step * (long long)ROW16);
+                const uint64_t w1res_desc = wres_desc - (uint64_t)u.n_stream * TAP16;   // resident conv1 tap j at + j * TAP16
+                const int n_stream = u.n_stream, taps1 = p.taps;
+                uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;
+                for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+                    VTTS_TRACE(0);
+                    // A[tl & 1] is free once the operand epilogue of tile tl-2 has read it
+                    mbar_wait(&accA_empty[tl & 1u], ((tl >> 1) & 1u) ^ 1u);
+                    mbar_wait(&act_full[sa], aph);
+                    VTTS_TRACE(10);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + ((tl & 1u) ? COL_A1 : 0u);
+                    uint64_t bdesc = act_desc + (uint64_t)sa * ACT16 + (uint64_t)tap0;
+                    uint32_t acc = 0;
+                    int j = 0;
+                    for (; j < n_stream; ++j) {                       // streamed taps (ring)
+                        mbar_wait(&w_full[sw], wph);
+                        tc_fence_after();
+                        const uint64_t adesc = wring_desc + (uint64_t)sw * TAP16;
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idescA, acc);
+                            acc = 1;
+                        }
+                        umma_commit(&w_empty[sw]);
+                        if (++sw == W_STAGES) { sw = 0; wph ^= 1u; }
+                        bdesc += tap_step;
+                    }
+                    uint64_t adesc = w1res_desc + (uint64_t)j * TAP16;
+                    for (; j < taps1; ++j) {                          // resident taps
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idescA, acc);
+                            acc = 1;
+                        }
+                        adesc += TAP16;
+                        bdesc += tap_step;
+                    }
+                    VTTS_TRACE(11);
+                    umma_commit(&act_empty[sa]);
+                    if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; }
+                    umma_commit(&accA_full[tl & 1u]);
+                    VTTS_TRACE(1);
+                }
+            } else {
+                const int h2 = (u.taps2 - 1) / 2;
+                const uint64_t xt_desc = make_smem_desc(smem_u32(s_xt), ROWB, 0) + (uint64_t)(V_XT_OFF - h2) * ROW16;
+                const uint64_t w2_desc = wres_desc + (uint64_t)(p.taps - u.n_stream) * TAP16;
+                const int taps2 = u.taps2;
+                uint32_t tl = 0;
+                for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+                    mbar_wait(xt_full, tl & 1u);                      // operand epilogue wrote the xt tile
+                    VTTS_TRACE(2);
+                    mbar_wait(&accB_empty[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // output epilogue of tile tl-2 drained B[tl & 1]
+                    VTTS_TRACE(3);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + ((tl & 1u) ? COL_B1 : COL_B0);
+                    uint64_t adesc = w2_desc, bdesc = xt_desc;
+                    uint32_t acc = 0;
+                    for (int j = 0; j < taps2; ++j) {
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idescB, acc);
+                            acc = 1;
+                        }
+                        adesc += TAP16;
+                        bdesc += ROW16;
+                    }
+                    umma_commit(xt_empty);                            // xt may be overwritten once these MMAs retire
+                    umma_commit(&accB_full[tl & 1u]);
+                    VTTS_TRACE(4);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps.  Quarter q of the TMEM lanes holds accumulator rows 16q .. 16q+15 in its first 16 lanes;
+        // row r is channel r % C (C = 32: two copies of every channel -> two warps per channel share the columns).
+        const int ew = warp, quarter = warp & 3;
+        const bool is_ea = ew < N_GRP;
+        const int chb = (quarter * 16) % p.cout;                      // first channel of this warp's 16 rows
+        const int copy = (quarter * 16) / p.cout;
+        const int n_workers = (V_M / p.cout) * (N_GRP / 4);           // warps sharing one channel set
+        const int worker = copy * (N_GRP / 4) + (ew % N_GRP) / 4;
+        const int fr = lane >> 2, fc = (lane & 3) * 2;                // fragment row (channel) / first column (position)
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t tl = 0;
+        if (is_ea) {
+            float b1[2];
+            b1[0] = u.bias1 ? __ldg(u.bias1 + chb + fr) : 0.f;
+            b1[1] = u.bias1 ? __ldg(u.bias1 + chb + fr + 8) : 0.f;
+            const uint32_t xt0 = smem_u32(s_xt);
+            const uint32_t cblk = (uint32_t)(chb / 8 + ((lane >> 3) & 1));   // 16-byte chunk written by matrix lane/8
+            const int mrow = (lane & 7) + 8 * (lane >> 4);                   // row (position) this thread addresses
+            for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+                const int i0 = w.t * VN_B;
+                mbar_wait_relaxed(&accA_full[tl & 1u], (tl >> 1) & 1u);
+                if (ew == 0 && lane == 0) VTTS_TRACE(5);
+                mbar_wait_relaxed(xt_empty, (tl & 1u) ^ 1u);          // conv2 of the previous tile finished reading xt
+                tc_fence_after();
+                const uint32_t t_acc = t_lane + ((tl & 1u) ? COL_A1 : 0u);
+                const int pos0 = i0 - V_XT_OFF;
+                const bool interior = pos0 >= 0 && pos0 + VN_A <= p.n_pos;
+                uint32_t r[8];
+                int col = worker * 16;
+                if (col < VN_A) tmem_ld_16x256_x2(t_acc + (uint32_t)col, r);
+                for (; col < VN_A; col += n_workers * 16) {
+                    tmem_ld_wait();
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = lrelu_max(__uint_as_float(r[e]) + b1[(e >> 1) & 1], u.slope_mid);
+                    const int col_n = col + n_workers * 16;
+                    if (col_n < VN_A) tmem_ld_16x256_x2(t_acc + (uint32_t)col_n, r);
+                    if (!interior) {                                  // conv2 zero-pads its own input
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int pos = pos0 + col + ((e >> 2) & 1) * 8 + fc + (e & 1);
+                            if (pos < 0 || pos >= p.n_pos) v[e] = 0.f;
+                        }
+                    }
+                    const int row = col + mrow;
+                    const uint32_t swz = ROWB == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                    stmatrix_x4_trans(xt0 + (uint32_t)row * ROWB + ((cblk ^ swz) << 4), cvt16x2(v[0], v[1], FMT),
+                                      cvt16x2(v[2], v[3], FMT), cvt16x2(v[4], v[5], FMT), cvt16x2(v[6], v[7], FMT));
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(xt_full); mbar_arrive(&accA_empty[tl & 1u]); }
+                if (ew == 0 && lane == 0) VTTS_TRACE(6);
+            }
+        } else {
+            const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
+                       A = p.out_a != nullptr;
+            const int mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX
+                           : (R && Cc && !D && X && !A) ? EPI_RCX : (R && Cc && D && X && A) ? EPI_RCDXA
+                           : (R && Cc && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
+            const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
+            const int odd = lane & 1;
+            const int ch = chb + fr + 8 * odd;                        // after the pair exchange a thread owns one channel
+            const int pg = (lane & 3) >> 1;                           // which group of 4 positions inside 8 columns
+            const float bias2 = p.bias ? __ldg(p.bias + ch) : 0.f;
+            const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
+            for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+                const int i0 = w.t * VN_B, b = w.b;
+                {   // L2 prefetch of the fp32 streams of the next live tile (contiguous in the time-packed layout)
+                    Walk wn = w;
+                    walk_next(wn);
+                    if (wn.item < p.total_tiles && (R || Cc)) {
+                        const int i0n = wn.t * VN_B, bn = wn.b;
+                        const int rows4 = min(VN_B / 4, p.L4 - i0n / 4);
+                        const long long off = ((long long)bn * p.L4 + i0n / 4) * p.cout * 4;
+                        const int n_lines = rows4 * p.cout / 8;
+                        for (int l = threadIdx.x - N_GRP * 32; l < n_lines; l += N_GRP * 32) {
+                            if (R) prefetch_l2(p.res + off + (long long)l * 32);
+                            if (Cc) prefetch_l2(p.out_x + off + (long long)l * 32);
+                        }
+                    }
+                }
+                auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && ibase + 16 <= n_valid; };
+                auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + ((ibase >> 2) + pg)) * p.cout + ch) * 4; };
+                auto load2 = [&](EpiLoads2 &d, const float *ptr) {
+                    d.r[0] = __ldg(reinterpret_cast<const float4 *>(ptr));
+                    d.r[1] = __ldg(reinterpret_cast<const float4 *>(ptr + (size_t)2 * p.cout * 4));
+                };
+                EpiLoads2 cur{}, nxt{};
+                const int col0 = worker * 16;
+                if (R && col0 < VN_B && group_fast(i0 + col0)) load2(nxt, res_ptr(i0 + col0));
+                if (ew == N_GRP && lane == 0) VTTS_TRACE(7);
+                mbar_wait_relaxed(&accB_full[tl & 1u], (tl >> 1) & 1u);
+                if (ew == N_GRP && lane == 0) VTTS_TRACE(8);
+                tc_fence_after();
+                const uint32_t t_acc = t_lane + ((tl & 1u) ? COL_B1 : COL_B0);
+                for (int col = col0; col < VN_B; col += n_workers * 16) {
+                    const int ibase = i0 + col;
+                    if (ibase >= p.n_pos) break;
+                    uint32_t r[8];
+                    tmem_ld_16x256_x2(t_acc + (uint32_t)col, r);
+                    cur = nxt;
+                    const bool fast = group_fast(ibase);
+                    const int col_n = col + n_workers * 16;
+                    if (R && col_n < VN_B && group_fast(i0 + col_n)) load2(nxt, res_ptr(i0 + col_n));
+                    tmem_ld_wait();
+                    // pair exchange: even lanes keep row fr and take the partner's two columns, odd lanes keep row
+                    // fr + 8; afterwards a thread holds 4 consecutive positions (twice, 8 apart) of one channel
+                    const uint32_t s0 = odd ? r[0] : r[2], s1 = odd ? r[1] : r[3], s2 = odd ? r[4] : r[6], s3 = odd ? r[5] : r[7];
+                    const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), y0 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                    const uint32_t x1 = __shfl_xor_sync(0xffffffffu, s2, 1), y1 = __shfl_xor_sync(0xffffffffu, s3, 1);
+                    float q[8];
+                    if (odd) {
+                        q[0] = __uint_as_float(x0); q[1] = __uint_as_float(y0); q[2] = __uint_as_float(r[2]); q[3] = __uint_as_float(r[3]);
+                        q[4] = __uint_as_float(x1); q[5] = __uint_as_float(y1); q[6] = __uint_as_float(r[6]); q[7] = __uint_as_float(r[7]);
+                    } else {
+                        q[0] = __uint_as_float(r[0]); q[1] = __uint_as_float(r[1]); q[2] = __uint_as_float(x0); q[3] = __uint_as_float(y0);
+                        q[4] = __uint_as_float(r[4]); q[5] = __uint_as_float(r[5]); q[6] = __uint_as_float(x1); q[7] = __uint_as_float(y1);
+                    }
+                    const int pos = ibase + pg * 4;                   // first of this thread's 4 positions
+                    if (fast) {
+                        float *px = X ? p.out_x + (((long long)b * p.L4 + (pos >> 2)) * p.cout + ch) * 4 : nullptr;
+                        uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + pos) * p.out_a_ld + ch : nullptr;
+                        epi64_pair_dispatch<FMT>(mode, c_ct, q, bias2, p, cur, px, pa);
+                    } else {
+                        epi64_pair_edge<FMT>(q, bias2, p, b, pos, ch);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&accB_empty[tl & 1u]);
+                if (ew == N_GRP && lane == 0) VTTS_TRACE(9);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+struct TcUnit64Launch {
+    CUtensorMap tm_act, tm_w1, tm_w2;
+    TcUnit64Params u;
+    int rowb, fmt;
+    dim3 grid;
+    size_t smem;
+};
+
+template <int ROWB, int FMT>
+static int unit64_launch_t(const TcUnit64Launch &L, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit64_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    unit64_tc_kernel<ROWB, FMT><<<L.grid, V_THREADS, L.smem, st>>>(L.tm_act, L.tm_w1, L.tm_w2, L.u);
+    VTTS_CHECK_LAUNCH();
+    return VTTS_OK;
+}
+static int unit64_launch(const TcUnit64Launch &L, cudaStream_t st) {
+    if (L.rowb == 128) return L.fmt == VTTS_FMT_BF16 ? unit64_launch_t<128, 0>(L, st) : unit64_launch_t<128, 1>(L, st);
+    return L.fmt == VTTS_FMT_BF16 ? unit64_launch_t<64, 0>(L, st) : unit64_launch_t<64, 1>(L, st);
+}
+
+static bool tc_unit64_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VTTS_TC_UNIT64"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+// shared-memory plan of the narrow unit: returns false when conv2 cannot be fully resident
+static bool unit64_plan(int C, int k1, int k2, int &act_stages, int &w_stages, int &n_stream, int &n_res, size_t &smem) {
+    const int rowb = C * 2;
+    const size_t tapb = (size_t)V_M * rowb, actb = (size_t)V_ACT_ROWS * rowb, xtb = (size_t)VN_A * rowb;
+    const size_t fixed = xtb + 512 + MAX_TRIM_BATCH * sizeof(int);
+    const size_t avail = 227 * 1024;
+    const int total = k1 + k2;
+    for (act_stages = 4; act_stages >= 2; --act_stages) {
+        w_stages = 0; n_stream = 0; n_res = total;
+        smem = fixed + act_stages * actb + (size_t)total * tapb;
+        if (smem <= avail) return true;
+    }
+    act_stages = 2; w_stages = 4;
+    const size_t base = fixed + act_stages * actb + w_stages * tapb;
+    if (base + (size_t)k2 * tapb > avail) return false;
+    n_res = (int)((avail - base) / tapb);
+    if (n_res > total) n_res = total;
+    n_stream = total - n_res;
+    if (n_stream > k1) return false;
+    smem = base + (size_t)n_res * tapb;
+    return true;
+}
+
+static bool unit64_usable(int C, int k1, int d1, int k2) {
+    if (!tc_unit64_enabled() || (C != 32 && C != 64)) return false;
+    if ((k1 - 1) * d1 > HALO_MAX || (k2 - 1) / 2 > V_XT_OFF || k2 < 1) return false;
+    int a, w, ns, nr;
+    size_t smem;
+    return unit64_plan(C, k1, k2, a, w, ns, nr, smem);
+}
+
+static int unit64_prepare(TcUnit64Launch &L, int fmt, const uint16_t *act, int B, int Lpos, int C, const uint16_t *w1, int k1,
+                          int d1, const float *bias1, float slope_mid, const uint16_t *w2, int k2, TcConvParams p) {
+    const int rowb = C * 2;
+    L.rowb = rowb; L.fmt = fmt;
+    p.n_total = C; p.cout = C; p.L_out = Lpos; p.n_pos = Lpos; p.out_stride = 1; p.out_off0 = 0;
+    p.taps = k1; p.tap_off0 = -(k1 - 1) / 2 * d1; p.tap_step = d1;
+    p.chunks = 1; p.m_blocks = 1; p.cluster = 1; p.groups_per_batch = 0;
+    p.t_tiles = ceil_div(Lpos, VN_B);
+    const long long total = (long long)p.t_tiles * B;
+    if (total > 0x7fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "tc: too many tiles");
+    p.total_tiles = (int)total;
+    p.inv_div = p.divide_by > 0.f ? 1.f / p.divide_by : 1.f;
+    p.rep = V_M / C; p.w_rows = V_M; p.epi_quarters = 4; p.tps = 1;
+    p.L4 = (Lpos + 3) / 4;
+    p.batch = B;
+    if (p.lens && B > MAX_TRIM_BATCH) p.lens = nullptr;
+    int act_stages, w_stages, n_stream, n_res;
+    if (!unit64_plan(C, k1, k2, act_stages, w_stages, n_stream, n_res, L.smem))
+        return set_error(VTTS_E_UNSUPPORTED, "tc unit64: weights of conv2 do not fit in shared memory");
+    p.act_stages = act_stages; p.w_stages = w_stages;
+    L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.n_stream = n_stream; L.u.n_res = n_res;
+    const int sms = tc_num_sms();
+    L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
+    {
+        uint64_t dims[3] = {(uint64_t)C, (uint64_t)Lpos, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * (uint64_t)Lpos};
+        uint32_t box[3] = {(uint32_t)C, BOX_ROWS, 1};
+        int rc = make_tmap_bf16(&L.tm_act, act, 3, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    for (int w = 0; w < 2; ++w) {
+        uint64_t dims[3] = {(uint64_t)C, (uint64_t)TM, (uint64_t)(w == 0 ? k1 : k2)};
+        uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * (uint64_t)TM};
+        uint32_t box[3] = {(uint32_t)C, (uint32_t)V_M, 1};
+        int rc = make_tmap_bf16(w == 0 ? &L.tm_w1 : &L.tm_w2, w == 0 ? w1 : w2, 3, dims, str, box, rowb);
+        if (rc) return rc;
+    }
+    return VTTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight packing: fp32 reference layout -> bf16 [tap][n_pad][ci_pad]
 // ---------------------------------------------------------------------------------------------
 // Conv1d (cout,cin,k): n = co, tap j = kernel index.
@@ -1459,9 +2001,13 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
         p.len_rate = rate;
         p.len_extra = 0;
     }
+    const bool narrow = unit64_usable(l1.info.cout, l1.info.ksize, l1.info.dilation, l2.info.ksize);
     TcUnitLaunch L;
-    int rc = unit_prepare(L, fmt, act, B, Lpos, l1.info.cout, l1.w16[fmt], l1.info.ksize, l1.info.dilation,
-                          l1.has_bias ? l1.bias : nullptr, slope_mid, l2.w16[fmt], l2.info.ksize, p);
+    TcUnit64Launch L64;
+    int rc = narrow ? unit64_prepare(L64, fmt, act, B, Lpos, l1.info.cout, l1.w16[fmt], l1.info.ksize, l1.info.dilation,
+                                     l1.has_bias ? l1.bias : nullptr, slope_mid, l2.w16[fmt], l2.info.ksize, p)
+                    : unit_prepare(L, fmt, act, B, Lpos, l1.info.cout, l1.w16[fmt], l1.info.ksize, l1.info.dilation,
+                                   l1.has_bias ? l1.bias : nullptr, slope_mid, l2.w16[fmt], l2.info.ksize, p);
     if (rc) return rc;
     ProfRec pr{};
     if (prof_enabled()) {
@@ -1470,8 +2016,8 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
         pr.B = B; pr.L = Lpos;
         cudaEventRecord(pr.a, st);
     }
-    if (g_trace_on >= 100 && h->launch_count == g_trace_on - 100) L.u.e.trace = 1;   // debug: trace this launch of the forward
-    if ((rc = unit_launch(L, st))) return rc;
+    if (g_trace_on >= 100 && h->launch_count == g_trace_on - 100) { L.u.e.trace = 1; L64.u.e.trace = 1; }   // debug: trace this launch
+    if ((rc = narrow ? unit64_launch(L64, st) : unit_launch(L, st))) return rc;
     if (prof_enabled()) { cudaEventRecord(pr.b, st); g_prof.push_back(pr); }
     h->launch_count++;
     return VTTS_OK;
@@ -1649,7 +2195,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *slot;
     if (threadIdx.x == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint32_t idesc = make_idesc_16((variant & 4) ? 64 : 128, N, 0);
         for (int kb = 0; kb < kblocks; ++kb) {
             mbar_arrive_expect_tx(bar_ld, (uint32_t)((128 + b_rows) * ROWB));
             tma_load_2d(s_a, &tm_a, bar_ld, kb * CH, 0);
@@ -1670,12 +2216,27 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     __syncthreads();
     tc_fence_after();
+    if (variant & 8) {
+        // readout through 16-lane mma-style fragments (tcgen05.ld 16x256b.x2), written back under the assumed layout
+        for (int h = 0; h < 2; ++h)
+            for (int col = 0; col < N; col += 16) {
+                uint32_t v[8];
+                tmem_ld_16x256_x2(tmem + ((uint32_t)(warp * 32 + h * 16) << 16) + (uint32_t)col, v);
+                tmem_ld_wait();
+                for (int e = 0; e < 8; ++e) {
+                    const int m = warp * 32 + h * 16 + (lane >> 2) + ((e >> 1) & 1) * 8;
+                    const int c = col + ((e >> 2) & 1) * 8 + (lane & 3) * 2 + (e & 1);
+                    d[(size_t)m * N + c] = __uint_as_float(v[e]);
+                }
+            }
+    } else {
     for (int col = 0; col < N; col += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
         tmem_ld_wait();
         const int m = warp * 32 + lane;
         for (int e = 0; e < 32; ++e) d[(size_t)m * N + col + e] = __uint_as_float(v[e]);
+    }
     }
     tc_fence_before();
     __syncthreads();
@@ -1688,7 +2249,7 @@ using namespace vtts::probe;
 extern "C" int vtts_dbg_umma_gemm(const void *a_bf16, const void *b_bf16, float *d, int M, int N, int K,
                                   int b_rows_total, int row_shift, int variant, vtts_stream_t stream) {
     VTTS_REQUIRE(a_bf16 && b_bf16 && d, "vtts_dbg_umma_gemm: null pointer");
-    VTTS_REQUIRE(M == 128, "vtts_dbg_umma_gemm: M must be 128");
+    VTTS_REQUIRE(M == 128, "vtts_dbg_umma_gemm: M must be 128 (variant bit 2 issues M=64 MMAs on the first 64 rows)");
     VTTS_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256, "vtts_dbg_umma_gemm: N must be a multiple of 32 in [32,256]");
     const int rowb = (variant & 2) ? 64 : 128;
     const int ch = rowb / 2;
