@@ -83,21 +83,19 @@ int launch_pack_convT_fp32(const float *w, float *packed, int cin, int cout, int
 // (B, C, L) fp32 channels-first <-> (B, L, C) channels-last
 // 16-bit operand formats of the tensor-core path
 enum { VTTS_FMT_BF16 = 0, VTTS_FMT_FP16 = 1 };
+// fp16 conversions saturate to the largest finite value instead of overflowing to inf (one F2FP.SATFINITE instruction)
 __device__ __forceinline__ uint16_t cvt16(float v, int fmt) {
     if (fmt == VTTS_FMT_BF16) return __bfloat16_as_ushort(__float2bfloat16(v));
-    v = fminf(fmaxf(v, -65504.f), 65504.f);  // saturate instead of overflowing to inf
-    return __half_as_ushort(__float2half_rn(v));
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
 }
 // two values -> one 32-bit register, `lo` in the low half (same rounding/saturation as cvt16)
 __device__ __forceinline__ uint32_t cvt16x2(float lo, float hi, int fmt) {
-    if (fmt == VTTS_FMT_BF16) {
-        const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-        return *reinterpret_cast<const uint32_t *>(&v);
-    }
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    const __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t *>(&v);
+    uint32_t r;
+    if (fmt == VTTS_FMT_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ float cvt16_to_f32(uint16_t u, int fmt) {
     return fmt == VTTS_FMT_BF16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));

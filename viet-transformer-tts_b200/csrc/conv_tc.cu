@@ -1181,6 +1181,8 @@ constexpr int VN_B = 112;          // conv2 output positions per tile (UMMA N of
 constexpr int V_XT_OFF = 8;        // xt row 0 is position i0 - 8
 constexpr int V_ACT_ROWS = 192;    // VN_A + dilation halo (<= 64)
 constexpr int V_M = 64;            // accumulator rows
+constexpr int V_BOX = 16;          // activation rows per TMA box (small boxes: the tile is fetched to the nearest 16 rows)
+constexpr int V_MAXG = 4;          // residual prefetch slots per output-epilogue warp (16-column groups in flight)
 constexpr int V_THREADS = (EPI_WARPS + 4) * 32;   // 16 epilogue warps, activation + weight producers, two MMA issuers
 
 struct TcUnit64Params {
@@ -1201,10 +1203,13 @@ __device__ __forceinline__ void epi64_pair(const float (&q)[8], float bias, cons
     using F = EpiFlags<MODE>;
     const int C = C_CT ? C_CT : p.cout;
     const int lda = C_CT ? C_CT : p.out_a_ld;
+    // running MRF sum: the middle blocks only add to it (vector reduction, nothing to wait for); the last block needs
+    // the value (mean + 16-bit copy) and loads it - both loads before the first store
+    constexpr bool RED = MODE == EPI_RCX;
     float4 accv[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
-        accv[m] = F::ACC ? *reinterpret_cast<const float4 *>(px + (size_t)m * 2 * C * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        accv[m] = (F::ACC && !RED) ? *reinterpret_cast<const float4 *>(px + (size_t)m * 2 * C * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
         float val[4];
@@ -1214,40 +1219,26 @@ __device__ __forceinline__ void epi64_pair(const float (&q)[8], float bias, cons
         for (int d = 0; d < 4; ++d) {
             float x = q[m * 4 + d] + bias;
             if (F::RES) x = x + rr[d];
-            if (F::ACC) x = aa[d] + x;
+            if (F::ACC && !RED) x = aa[d] + x;
             if (F::DIV) x = x * p.inv_div;
             val[d] = x;
         }
-        if (F::X) *reinterpret_cast<float4 *>(px + (size_t)m * 2 * C * 4) = make_float4(val[0], val[1], val[2], val[3]);
+        if (RED) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(px + (size_t)m * 2 * C * 4), "f"(val[0]),
+                         "f"(val[1]), "f"(val[2]), "f"(val[3])
+                         : "memory");
+        } else if (F::X) {
+            *reinterpret_cast<float4 *>(px + (size_t)m * 2 * C * 4) = make_float4(val[0], val[1], val[2], val[3]);
+        }
         if (F::A) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) pa[(size_t)(m * 8 + d) * lda] = cvt16(lrelu_max(val[d], p.slope_out), FMT);
         }
     }
 }
-template <int FMT, int MODE>
-__device__ __forceinline__ void epi64_pair_c(int c_ct, const float (&q)[8], float bias, const TcConvParams &p,
-                                             const EpiLoads2 &res, float *px, uint16_t *pa) {
-    switch (c_ct) {
-        case 32: epi64_pair<FMT, 32, MODE>(q, bias, p, res, px, pa); return;
-        case 64: epi64_pair<FMT, 64, MODE>(q, bias, p, res, px, pa); return;
-        default: epi64_pair<FMT, 0, MODE>(q, bias, p, res, px, pa); return;
-    }
-}
-template <int FMT>
-__device__ __forceinline__ void epi64_pair_dispatch(int mode, int c_ct, const float (&q)[8], float bias, const TcConvParams &p,
-                                                    const EpiLoads2 &res, float *px, uint16_t *pa) {
-    switch (mode) {
-        case EPI_RXA: epi64_pair_c<FMT, EPI_RXA>(c_ct, q, bias, p, res, px, pa); return;
-        case EPI_RX: epi64_pair_c<FMT, EPI_RX>(c_ct, q, bias, p, res, px, pa); return;
-        case EPI_RCX: epi64_pair_c<FMT, EPI_RCX>(c_ct, q, bias, p, res, px, pa); return;
-        case EPI_RCDXA: epi64_pair_c<FMT, EPI_RCDXA>(c_ct, q, bias, p, res, px, pa); return;
-        default: epi64_pair_c<FMT, EPI_RCDX>(c_ct, q, bias, p, res, px, pa); return;
-    }
-}
 // per-element path (tile edges, unusual epilogue combinations)
 template <int FMT>
-__device__ __forceinline__ void epi64_pair_edge(const float (&q)[8], float bias, const TcConvParams &p, int b, int pos0, int ch) {
+__device__ __noinline__ void epi64_pair_edge(const float (&q)[8], float bias, const TcConvParams &p, int b, int pos0, int ch) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int t = pos0 + (e >> 2) * 8 + (e & 3);
@@ -1263,7 +1254,9 @@ __device__ __forceinline__ void epi64_pair_edge(const float (&q)[8], float bias,
     }
 }
 
-template <int ROWB, int FMT>
+// MODE: the output epilogue variant (EPI_*), compile-time so that each instantiation carries one epilogue body - the
+// instruction-cache footprint of the 20 concurrently running warps matters.
+template <int ROWB, int FMT, int MODE>
 __global__ void __launch_bounds__(V_THREADS, 1)
 unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const TcUnit64Params u) {
@@ -1281,15 +1274,15 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     uint8_t *s_wres = s_act + (size_t)ACT_STAGES * ACT_BYTES;
     uint8_t *s_wring = s_wres + (size_t)u.n_res * TAPB;
     uint8_t *s_xt = s_wring + (size_t)W_STAGES * TAPB;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + XT_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + 2 * XT_BYTES);     // two xt buffers
     uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
     uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
     uint64_t *wres_full = w_empty + W_STAGES;
-    uint64_t *accA_full = wres_full + 1;          // [2]
-    uint64_t *accA_empty = accA_full + 2;         // [2]
-    uint64_t *xt_full = accA_empty + 2, *xt_empty = xt_full + 1;
-    uint64_t *accB_full = xt_empty + 1;           // [2]
-    uint64_t *accB_empty = accB_full + 2;         // [2]
+    // per buffer (tile parity): accA_full  conv1 MMAs done          -> operand epilogue may read A[b]
+    //                            xt_full    operand epilogue done    -> conv2 may read xt[b]; conv1 may overwrite A[b]
+    //                            accB_full  conv2 MMAs done          -> output epilogue may read B[b]; xt[b] may be rewritten
+    //                            accB_empty output epilogue done     -> conv2 may overwrite B[b]
+    uint64_t *accA_full = wres_full + 1, *xt_full = accA_full + 2, *accB_full = xt_full + 2, *accB_empty = accB_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 2);
     int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
 
@@ -1297,7 +1290,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
-    const int nbox = (VN_A + span + BOX_ROWS - 1) / BOX_ROWS;
+    const int nbox = (VN_A + span + V_BOX - 1) / V_BOX;
     const int ncta = (int)gridDim.x;
     constexpr int N_GRP = EPI_WARPS / 2;          // warps per epilogue group
 
@@ -1323,8 +1316,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(wres_full, 1);
         mbar_init(&accA_full[0], 1); mbar_init(&accA_full[1], 1);
-        mbar_init(&accA_empty[0], N_GRP); mbar_init(&accA_empty[1], N_GRP);
-        mbar_init(xt_full, N_GRP); mbar_init(xt_empty, 1);
+        mbar_init(&xt_full[0], N_GRP); mbar_init(&xt_full[1], N_GRP);
         mbar_init(&accB_full[0], 1); mbar_init(&accB_full[1], 1);
         mbar_init(&accB_empty[0], N_GRP); mbar_init(&accB_empty[1], N_GRP);
         fence_barrier_init();
@@ -1347,11 +1339,19 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             uint32_t s = 0, ph = 0;
             for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w)) {
                 const int i0 = w.t * VN_B, b = w.b;
+                {   // the fp32 streams the output epilogue of this tile will read (residual, running MRF sum) are one
+                    // contiguous block in the time-packed layout: pull it into L2 now, several tiles ahead of its use
+                    const int rows4 = min(VN_B / 4, p.L4 - i0 / 4);
+                    const long long off = ((long long)b * p.L4 + i0 / 4) * p.cout * 4;
+                    const uint32_t bytes = (uint32_t)rows4 * (uint32_t)p.cout * 16u;
+                    if (p.res) bulk_prefetch_l2(p.res + off, bytes);
+                    if (p.accumulate && p.divide_by > 0.f) bulk_prefetch_l2(p.out_x + off, bytes);
+                }
                 mbar_wait(&act_empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
+                mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * V_BOX * ROWB));
                 for (int bx = 0; bx < nbox; ++bx)
-                    tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s], 0,
-                                i0 - V_XT_OFF + min_off + bx * BOX_ROWS, b);
+                    tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * V_BOX * ROWB, &tm_act, &act_full[s], 0,
+                                i0 - V_XT_OFF + min_off + bx * V_BOX, b);
                 if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -1397,7 +1397,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
                     VTTS_TRACE(0);
                     // A[tl & 1] is free once the operand epilogue of tile tl-2 has read it
-                    mbar_wait(&accA_empty[tl & 1u], ((tl >> 1) & 1u) ^ 1u);
+                    mbar_wait(&xt_full[tl & 1u], ((tl >> 1) & 1u) ^ 1u);
                     mbar_wait(&act_full[sa], aph);
                     VTTS_TRACE(10);
                     tc_fence_after();
@@ -1437,17 +1437,18 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             } else {
                 const int h2 = (u.taps2 - 1) / 2;
                 const uint64_t xt_desc = make_smem_desc(smem_u32(s_xt), ROWB, 0) + (uint64_t)(V_XT_OFF - h2) * ROW16;
+                constexpr uint64_t XT16 = (uint64_t)(XT_BYTES >> 4);
                 const uint64_t w2_desc = wres_desc + (uint64_t)(p.taps - u.n_stream) * TAP16;
                 const int taps2 = u.taps2;
                 uint32_t tl = 0;
                 for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
-                    mbar_wait(xt_full, tl & 1u);                      // operand epilogue wrote the xt tile
+                    mbar_wait(&xt_full[tl & 1u], (tl >> 1) & 1u);     // operand epilogue wrote xt[tl & 1]
                     VTTS_TRACE(2);
                     mbar_wait(&accB_empty[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // output epilogue of tile tl-2 drained B[tl & 1]
                     VTTS_TRACE(3);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + ((tl & 1u) ? COL_B1 : COL_B0);
-                    uint64_t adesc = w2_desc, bdesc = xt_desc;
+                    uint64_t adesc = w2_desc, bdesc = xt_desc + ((tl & 1u) ? XT16 : 0);
                     uint32_t acc = 0;
                     for (int j = 0; j < taps2; ++j) {
 #pragma unroll
@@ -1458,7 +1459,6 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         adesc += TAP16;
                         bdesc += ROW16;
                     }
-                    umma_commit(xt_empty);                            // xt may be overwritten once these MMAs retire
                     umma_commit(&accB_full[tl & 1u]);
                     VTTS_TRACE(4);
                 }
@@ -1480,16 +1480,17 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             float b1[2];
             b1[0] = u.bias1 ? __ldg(u.bias1 + chb + fr) : 0.f;
             b1[1] = u.bias1 ? __ldg(u.bias1 + chb + fr + 8) : 0.f;
-            const uint32_t xt0 = smem_u32(s_xt);
+            const uint32_t xt_base = smem_u32(s_xt);
             const uint32_t cblk = (uint32_t)(chb / 8 + ((lane >> 3) & 1));   // 16-byte chunk written by matrix lane/8
             const int mrow = (lane & 7) + 8 * (lane >> 4);                   // row (position) this thread addresses
             for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
                 const int i0 = w.t * VN_B;
                 mbar_wait_relaxed(&accA_full[tl & 1u], (tl >> 1) & 1u);
                 if (ew == 0 && lane == 0) VTTS_TRACE(5);
-                mbar_wait_relaxed(xt_empty, (tl & 1u) ^ 1u);          // conv2 of the previous tile finished reading xt
+                mbar_wait_relaxed(&accB_full[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // conv2 of tile tl-2 finished reading xt[tl & 1]
                 tc_fence_after();
                 const uint32_t t_acc = t_lane + ((tl & 1u) ? COL_A1 : 0u);
+                const uint32_t xt0 = xt_base + ((tl & 1u) ? (uint32_t)XT_BYTES : 0u);
                 const int pos0 = i0 - V_XT_OFF;
                 const bool interior = pos0 >= 0 && pos0 + VN_A <= p.n_pos;
                 uint32_t r[8];
@@ -1517,16 +1518,12 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(xt_full); mbar_arrive(&accA_empty[tl & 1u]); }
+                if (lane == 0) mbar_arrive(&xt_full[tl & 1u]);
                 if (ew == 0 && lane == 0) VTTS_TRACE(6);
             }
         } else {
-            const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr,
-                       A = p.out_a != nullptr;
-            const int mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX
-                           : (R && Cc && !D && X && !A) ? EPI_RCX : (R && Cc && D && X && A) ? EPI_RCDXA
-                           : (R && Cc && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
-            const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
+            using F = EpiFlags<MODE>;
+            constexpr bool R = MODE != EPI_GENERIC && F::RES, X = F::X, A = F::A;   // GENERIC: per-element path only
             const int odd = lane & 1;
             const int ch = chb + fr + 8 * odd;                        // after the pair exchange a thread owns one channel
             const int pg = (lane & 3) >> 1;                           // which group of 4 positions inside 8 columns
@@ -1534,43 +1531,33 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
             for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
                 const int i0 = w.t * VN_B, b = w.b;
-                {   // L2 prefetch of the fp32 streams of the next live tile (contiguous in the time-packed layout)
-                    Walk wn = w;
-                    walk_next(wn);
-                    if (wn.item < p.total_tiles && (R || Cc)) {
-                        const int i0n = wn.t * VN_B, bn = wn.b;
-                        const int rows4 = min(VN_B / 4, p.L4 - i0n / 4);
-                        const long long off = ((long long)bn * p.L4 + i0n / 4) * p.cout * 4;
-                        const int n_lines = rows4 * p.cout / 8;
-                        for (int l = threadIdx.x - N_GRP * 32; l < n_lines; l += N_GRP * 32) {
-                            if (R) prefetch_l2(p.res + off + (long long)l * 32);
-                            if (Cc) prefetch_l2(p.out_x + off + (long long)l * 32);
-                        }
-                    }
-                }
-                auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && ibase + 16 <= n_valid; };
+                auto group_fast = [&](int ibase) { return MODE != EPI_GENERIC && ibase + 16 <= n_valid; };
                 auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + ((ibase >> 2) + pg)) * p.cout + ch) * 4; };
                 auto load2 = [&](EpiLoads2 &d, const float *ptr) {
                     d.r[0] = __ldg(reinterpret_cast<const float4 *>(ptr));
                     d.r[1] = __ldg(reinterpret_cast<const float4 *>(ptr + (size_t)2 * p.cout * 4));
                 };
-                EpiLoads2 cur{}, nxt{};
-                const int col0 = worker * 16;
-                if (R && col0 < VN_B && group_fast(i0 + col0)) load2(nxt, res_ptr(i0 + col0));
+                // all residual loads of this warp's groups go out before waiting for the accumulator
+                EpiLoads2 rl[V_MAXG];
+                const int col0 = worker * 16, cstep = n_workers * 16;
+#pragma unroll
+                for (int g = 0; g < V_MAXG; ++g) {
+                    const int col = col0 + g * cstep;
+                    rl[g] = EpiLoads2{};
+                    if (R && col < VN_B && group_fast(i0 + col)) load2(rl[g], res_ptr(i0 + col));
+                }
                 if (ew == N_GRP && lane == 0) VTTS_TRACE(7);
                 mbar_wait_relaxed(&accB_full[tl & 1u], (tl >> 1) & 1u);
                 if (ew == N_GRP && lane == 0) VTTS_TRACE(8);
                 tc_fence_after();
                 const uint32_t t_acc = t_lane + ((tl & 1u) ? COL_B1 : COL_B0);
-                for (int col = col0; col < VN_B; col += n_workers * 16) {
+                uint32_t r[8];
+                if (col0 < VN_B) tmem_ld_16x256_x2(t_acc + (uint32_t)col0, r);
+#pragma unroll
+                for (int g = 0; g < V_MAXG; ++g) {
+                    const int col = col0 + g * cstep;
+                    if (col >= VN_B) break;
                     const int ibase = i0 + col;
-                    if (ibase >= p.n_pos) break;
-                    uint32_t r[8];
-                    tmem_ld_16x256_x2(t_acc + (uint32_t)col, r);
-                    cur = nxt;
-                    const bool fast = group_fast(ibase);
-                    const int col_n = col + n_workers * 16;
-                    if (R && col_n < VN_B && group_fast(i0 + col_n)) load2(nxt, res_ptr(i0 + col_n));
                     tmem_ld_wait();
                     // pair exchange: even lanes keep row fr and take the partner's two columns, odd lanes keep row
                     // fr + 8; afterwards a thread holds 4 consecutive positions (twice, 8 apart) of one channel
@@ -1585,15 +1572,18 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         q[0] = __uint_as_float(r[0]); q[1] = __uint_as_float(r[1]); q[2] = __uint_as_float(x0); q[3] = __uint_as_float(y0);
                         q[4] = __uint_as_float(r[4]); q[5] = __uint_as_float(r[5]); q[6] = __uint_as_float(x1); q[7] = __uint_as_float(y1);
                     }
+                    if (col + cstep < VN_B) tmem_ld_16x256_x2(t_acc + (uint32_t)(col + cstep), r);   // next group's accumulators
+                    if (ibase >= p.n_pos) continue;
                     const int pos = ibase + pg * 4;                   // first of this thread's 4 positions
-                    if (fast) {
+                    if (group_fast(ibase)) {
                         float *px = X ? p.out_x + (((long long)b * p.L4 + (pos >> 2)) * p.cout + ch) * 4 : nullptr;
                         uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + pos) * p.out_a_ld + ch : nullptr;
-                        epi64_pair_dispatch<FMT>(mode, c_ct, q, bias2, p, cur, px, pa);
+                        epi64_pair<FMT, CH, MODE == EPI_GENERIC ? EPI_RX : MODE>(q, bias2, p, rl[g], px, pa);
                     } else {
                         epi64_pair_edge<FMT>(q, bias2, p, b, pos, ch);
                     }
                 }
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&accB_empty[tl & 1u]);
@@ -1609,21 +1599,32 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
 struct TcUnit64Launch {
     CUtensorMap tm_act, tm_w1, tm_w2;
     TcUnit64Params u;
-    int rowb, fmt;
+    int rowb, fmt, mode;
     dim3 grid;
     size_t smem;
 };
 
-template <int ROWB, int FMT>
-static int unit64_launch_t(const TcUnit64Launch &L, cudaStream_t st) {
+template <int ROWB, int FMT, int MODE>
+static int unit64_launch_m(const TcUnit64Launch &L, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit64_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit64_tc_kernel<ROWB, FMT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    unit64_tc_kernel<ROWB, FMT><<<L.grid, V_THREADS, L.smem, st>>>(L.tm_act, L.tm_w1, L.tm_w2, L.u);
+    unit64_tc_kernel<ROWB, FMT, MODE><<<L.grid, V_THREADS, L.smem, st>>>(L.tm_act, L.tm_w1, L.tm_w2, L.u);
     VTTS_CHECK_LAUNCH();
     return VTTS_OK;
+}
+template <int ROWB, int FMT>
+static int unit64_launch_t(const TcUnit64Launch &L, cudaStream_t st) {
+    switch (L.mode) {
+        case EPI_RXA: return unit64_launch_m<ROWB, FMT, EPI_RXA>(L, st);
+        case EPI_RX: return unit64_launch_m<ROWB, FMT, EPI_RX>(L, st);
+        case EPI_RCX: return unit64_launch_m<ROWB, FMT, EPI_RCX>(L, st);
+        case EPI_RCDXA: return unit64_launch_m<ROWB, FMT, EPI_RCDXA>(L, st);
+        case EPI_RCDX: return unit64_launch_m<ROWB, FMT, EPI_RCDX>(L, st);
+        default: return unit64_launch_m<ROWB, FMT, EPI_GENERIC>(L, st);
+    }
 }
 static int unit64_launch(const TcUnit64Launch &L, cudaStream_t st) {
     if (L.rowb == 128) return L.fmt == VTTS_FMT_BF16 ? unit64_launch_t<128, 0>(L, st) : unit64_launch_t<128, 1>(L, st);
@@ -1639,7 +1640,7 @@ static bool tc_unit64_enabled() {
 // shared-memory plan of the narrow unit: returns false when conv2 cannot be fully resident
 static bool unit64_plan(int C, int k1, int k2, int &act_stages, int &w_stages, int &n_stream, int &n_res, size_t &smem) {
     const int rowb = C * 2;
-    const size_t tapb = (size_t)V_M * rowb, actb = (size_t)V_ACT_ROWS * rowb, xtb = (size_t)VN_A * rowb;
+    const size_t tapb = (size_t)V_M * rowb, actb = (size_t)V_ACT_ROWS * rowb, xtb = (size_t)2 * VN_A * rowb;
     const size_t fixed = xtb + 512 + MAX_TRIM_BATCH * sizeof(int);
     const size_t avail = 227 * 1024;
     const int total = k1 + k2;
@@ -1688,12 +1689,18 @@ static int unit64_prepare(TcUnit64Launch &L, int fmt, const uint16_t *act, int B
         return set_error(VTTS_E_UNSUPPORTED, "tc unit64: weights of conv2 do not fit in shared memory");
     p.act_stages = act_stages; p.w_stages = w_stages;
     L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.n_stream = n_stream; L.u.n_res = n_res;
+    {
+        const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr, A = p.out_a != nullptr;
+        L.mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX : (R && Cc && !D && X && !A) ? EPI_RCX
+               : (R && Cc && D && X && A) ? EPI_RCDXA : (R && Cc && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
+        if (A && p.out_a_ld != C) L.mode = EPI_GENERIC;        // the fast epilogue assumes a dense 16-bit copy
+    }
     const int sms = tc_num_sms();
     L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     {
         uint64_t dims[3] = {(uint64_t)C, (uint64_t)Lpos, (uint64_t)B};
         uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * (uint64_t)Lpos};
-        uint32_t box[3] = {(uint32_t)C, BOX_ROWS, 1};
+        uint32_t box[3] = {(uint32_t)C, (uint32_t)V_BOX, 1};
         int rc = make_tmap_bf16(&L.tm_act, act, 3, dims, str, box, rowb);
         if (rc) return rc;
     }

@@ -40,14 +40,16 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t p
         : "memory");
     return ok != 0;
 }
+// out of line: the diagnostic must not bloat every wait site (instruction-cache footprint of the big kernels)
+static __device__ __noinline__ void mbar_timeout() {
+    printf("vtts: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
     if (mbar_try_wait_addr(bar_addr, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait_addr(bar_addr, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("vtts: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) mbar_timeout();
     }
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
@@ -66,11 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s
-            printf("vtts: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) mbar_timeout();  // ~2 s
     }
 }
 
@@ -92,11 +90,13 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait_hint(bar, parity, 2000000u)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("vtts: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) mbar_timeout();
     }
+}
+
+// bulk L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): one instruction by one thread
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
