@@ -41,6 +41,43 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The generator is a chain of ~60 dependent kernels.  Each one is launched with the programmatic-serialization
+// attribute: its CTAs may become resident while the previous kernel drains and run their prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, resident weight loads - nothing the previous kernel produces); grid_dep_wait()
+// then blocks until the previous grid has completed and its writes are visible.  grid_dep_launch() is issued only
+// AFTER the wait, so by induction everything older than the previous kernel is complete before any prologue runs.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // VTTS_PDL=0 disables (conv_tc.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                           bool pdl, unsigned cluster_x, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    unsigned n = 0;
+    if (cluster_x > 1) {
+        attrs[n].id = cudaLaunchAttributeClusterDimension;
+        attrs[n].val.clusterDim.x = cluster_x;
+        attrs[n].val.clusterDim.y = 1;
+        attrs[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl) {
+        attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // ---------------------------------------------------------------------------------------

@@ -351,6 +351,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_after();
     if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     const uint32_t tmem_base = *tmem_slot;
+    grid_dep_wait();      // everything above overlapped the previous kernel's tail (programmatic dependent launch)
+    grid_dep_launch();
 
     if (warp == WARP_ACT) {
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
@@ -620,6 +622,7 @@ struct TcLaunch {
     CUtensorMap tm_act, tm_w;
     TcConvParams p;
     int rowb, fmt;
+    bool pdl = false;          // launch with programmatic stream serialization (forward chain only)
     dim3 grid;
     size_t smem;
 };
@@ -653,19 +656,8 @@ static int tc_launch_t(const TcLaunch &L, cudaStream_t st) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = L.grid;
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = L.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = (unsigned)L.p.cluster;
-    attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 1;
-    cfg.attrs = attrs;
-    cfg.numAttrs = 1;
-    VTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<ROWB, FMT>, L.tm_act, L.tm_w, L.p));
+    VTTS_CHECK_CUDA(launch_kernel_ex(conv_tc_kernel<ROWB, FMT>, L.grid, dim3(TC_THREADS), L.smem, st, L.pdl, (unsigned)L.p.cluster, L.tm_act,
+                                     L.tm_w, L.p));
     return VTTS_OK;
 }
 
@@ -816,6 +808,8 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tps = p.tps;
+    grid_dep_wait();      // the prologue above overlapped the previous kernel's tail
+    grid_dep_launch();
 
     if (warp == WARP_ACT) {
         if (lane == 0) {
@@ -1082,6 +1076,7 @@ struct TcUnitLaunch {
     CUtensorMap tm_act, tm_w1, tm_w2;
     TcUnitParams u;
     int rowb, fmt;
+    bool pdl = false;
     dim3 grid;
     size_t smem;
 };
@@ -1093,8 +1088,7 @@ static int unit_launch_t(const TcUnitLaunch &L, cudaStream_t st) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    unit_tc_kernel<ROWB, FMT><<<L.grid, TC_THREADS, L.smem, st>>>(L.tm_act, L.tm_w1, L.tm_w2, L.u);
-    VTTS_CHECK_LAUNCH();
+    VTTS_CHECK_CUDA(launch_kernel_ex(unit_tc_kernel<ROWB, FMT>, L.grid, dim3(TC_THREADS), L.smem, st, L.pdl, 1u, L.tm_act, L.tm_w1, L.tm_w2, L.u));
     return VTTS_OK;
 }
 
@@ -1332,6 +1326,9 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: the prologue above - and the resident weight loads below, which do not depend on
+    // the previous kernel - overlap that kernel's tail; everything else waits for it here
+    if (warp != WARP_W) { grid_dep_wait(); grid_dep_launch(); }
 
     if (warp == WARP_ACT) {
         if (lane == 0) {
@@ -1364,6 +1361,10 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             int slot = 0;
             for (int j = u.n_stream; j < p.taps; ++j, ++slot) tma_load_3d(s_wres + (size_t)slot * TAPB, &tm_w1, wres_full, 0, 0, j);
             for (int j = 0; j < u.taps2; ++j, ++slot) tma_load_3d(s_wres + (size_t)slot * TAPB, &tm_w2, wres_full, 0, 0, j);
+        }
+        grid_dep_wait();
+        grid_dep_launch();
+        if (lane == 0) {
             if (u.n_stream > 0) {
                 uint32_t s = 0, ph = 0;
                 for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w))
@@ -1600,6 +1601,7 @@ struct TcUnit64Launch {
     CUtensorMap tm_act, tm_w1, tm_w2;
     TcUnit64Params u;
     int rowb, fmt, mode;
+    bool pdl = false;
     dim3 grid;
     size_t smem;
 };
@@ -1611,8 +1613,8 @@ static int unit64_launch_m(const TcUnit64Launch &L, cudaStream_t st) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit64_tc_kernel<ROWB, FMT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    unit64_tc_kernel<ROWB, FMT, MODE><<<L.grid, V_THREADS, L.smem, st>>>(L.tm_act, L.tm_w1, L.tm_w2, L.u);
-    VTTS_CHECK_LAUNCH();
+    VTTS_CHECK_CUDA(launch_kernel_ex(unit64_tc_kernel<ROWB, FMT, MODE>, L.grid, dim3(V_THREADS), L.smem, st, L.pdl, 1u, L.tm_act, L.tm_w1, L.tm_w2,
+                                     L.u));
     return VTTS_OK;
 }
 template <int ROWB, int FMT>
@@ -1752,6 +1754,8 @@ conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /*
                      const long long *__restrict__ lens, int len_margin, int len_rate) {
     extern __shared__ float s_tile[];  // [(256 + 8)][C + 1] rows = time t0-4 .. t0+259
     const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;   // h <= 4
+    grid_dep_wait();
+    grid_dep_launch();
     if (lens != nullptr && (long long)t0 >= (lens[b] + len_margin) * (long long)len_rate) {
         // trimmed padding: defined (zero) output, no work
         const int t = t0 + threadIdx.x;
@@ -1807,6 +1811,11 @@ static int launch_cf_to_tp4(const float *x, float *y, int B, int C, int L, cudaS
 }
 
 }  // namespace tc
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VTTS_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // handle integration
@@ -1986,6 +1995,7 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
     TcLaunch L;
     int rc = tc_prepare(L, fmt, act, B, L_in, l.ci_pad, l.w16[fmt], pad_to(l.n_total, TM), p);
     if (rc) return rc;
+    L.pdl = pdl_enabled() && !prof_enabled();
     ProfRec pr{};
     if (prof_enabled()) {
         cudaEventCreate(&pr.a); cudaEventCreate(&pr.b);
@@ -2023,6 +2033,7 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
         pr.B = B; pr.L = Lpos;
         cudaEventRecord(pr.a, st);
     }
+    L.pdl = L64.pdl = pdl_enabled() && !prof_enabled();
     if (g_trace_on >= 100 && h->launch_count == g_trace_on - 100) { L.u.e.trace = 1; L64.u.e.trace = 1; }   // debug: trace this launch
     if ((rc = narrow ? unit64_launch(L64, st) : unit_launch(L, st))) return rc;
     if (prof_enabled()) { cudaEventRecord(pr.b, st); g_prof.push_back(pr); }
@@ -2142,6 +2153,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         const Layer &post = h->layers[h->idx_post];
         const int C = post.info.cin, k = post.info.ksize;
         const float *wt = post.w_aux;  // [oc][k][ci], packed at load time
+        const bool pdl = pdl_enabled() && !prof_enabled();
         dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
         if (k > 9) return set_error(VTTS_E_UNSUPPORTED, "conv_post: kernel size %d > 9", k);
         const size_t smem = (size_t)(256 + 8) * (C + 1) * sizeof(float);
@@ -2152,8 +2164,8 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
     do {                                                                                                      \
         if (smem > 48 * 1024)                                                                                 \
             VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tp4_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv_post_tp4_kernel<CC><<<grid, 256, smem, st>>>(bf.x_cs, w_oc, bias, wav, L, (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc, \
-                                                          trim_lens, h->trim_margin, rate); \
+        VTTS_CHECK_CUDA(launch_kernel_ex(conv_post_tp4_kernel<CC>, grid, dim3(256), smem, st, pdl, 1u, (const float *)bf.x_cs, w_oc, bias, wav, L, \
+                                         (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc, trim_lens, h->trim_margin, rate)); \
     } while (0)
             if (C == 32) VTTS_POST(32);
             else if (C == 64) VTTS_POST(64);
