@@ -48,9 +48,8 @@ static __device__ __noinline__ void mbar_timeout() {
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
     if (mbar_try_wait_addr(bar_addr, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_addr(bar_addr, parity)) {
-        if (clock64() - t0 > 4000000000LL) mbar_timeout();
-    }
+    for (uint32_t spins = 1; !mbar_try_wait_addr(bar_addr, parity); ++spins)   // clock checked every 64 probes: short loop
+        if ((spins & 63u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout();
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -67,9 +66,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) mbar_timeout();  // ~2 s
-    }
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins)
+        if ((spins & 63u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout();  // ~2 s
 }
 
 // Relaxed wait for warps that are not on the critical path (epilogue): the hardware suspends the
@@ -89,9 +87,8 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_hint(bar, parity, 2000000u)) {
-        if (clock64() - t0 > 4000000000LL) mbar_timeout();
-    }
+    for (uint32_t spins = 1; !mbar_try_wait_hint(bar, parity, 2000000u); ++spins)
+        if ((spins & 63u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout();
 }
 
 // bulk L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): one instruction by one thread
