@@ -325,6 +325,17 @@ def main():
         needed_frames = int(torch.clamp(ds.sum(1) + margin, max=T_out).sum()) if trim else padded_frames
         flops = needed_frames * FLOP_PER_FRAME_V1
         achieved = flops / (gen_avg_ms * 1e-3) / 1e12
+        # DRAM bytes of the same launch set: ncu launch list of the untrimmed forward at this shape (profiles/), scaled by
+        # the fraction of frames the trimmed step computes (traffic is proportional to the tiles processed)
+        traffic_bytes, traffic_note = None, "no ncu capture committed"
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+                tj = json.load(fh)
+            traffic_bytes = tj["dram_bytes_per_forward"] * needed_frames / float(16 * 759)
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum over the 52 launches of one forward "
+                            "(profiles/r01_launch_list.csv, B=16 x 759 frames untrimmed), scaled by frames computed / 12144")
+        except Exception:
+            pass
         value = audio_all * args.steps / (total_ms_all * 1e-3)
         line = {
             "metric": "synthesized audio sec/sec (inverse RTF)", "value": value, "unit": "audio_s/s",
@@ -350,9 +361,10 @@ def main():
                     "ms_per_step": e2e_ms_all / args.steps},
             "gpu_launches": launches_per_step * args.steps * world,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tc_peak, "traffic": None,
+                         "frac": achieved / tc_peak, "traffic": traffic_bytes,
                          "kernel": "generator conv kernels (all launches of one forward)",
-                         "flops_per_launch_set": flops, "ms": gen_avg_ms, "peak_source": peak_src},
+                         "flops_per_launch_set": flops, "ms": gen_avg_ms, "peak_source": peak_src,
+                         "traffic_source": traffic_note},
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -5,37 +5,53 @@ OUT = os.path.join(ROOT, "profiles"); G = os.path.join(ROOT, "gpurun_out")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 os.makedirs(OUT, exist_ok=True)
 
-# 1. launch list (ncu --metrics gpu__time_duration.sum, cold-cache, serialised): keep as CSV + share table
-rows = []
+# 1. launch list (ncu --metrics gpu__time_duration.sum,dram bytes; cold-cache, serialised): CSV + share table
+per = {}
 with open(os.path.join(G, "launches.csv")) as fh:
     lines = [l for l in fh if l.startswith('"')]
 for r in csv.DictReader(lines):
-    rows.append((int(r["ID"]), r["Kernel Name"].split("(")[0], r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3))
+    d = per.setdefault(int(r["ID"]), {"kernel": r["Kernel Name"].split("(")[0], "grid": r["Grid Size"], "block": r["Block Size"]})
+    v = float(r["Metric Value"].replace(",", ""))
+    unit = r["Metric Unit"]
+    if r["Metric Name"] == "gpu__time_duration.sum":
+        d["us"] = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+    else:
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        d[r["Metric Name"]] = v * mult
+rows = [(i, d["kernel"], d["grid"], d["block"], d.get("us", 0.0), d.get("dram__bytes_read.sum", 0.0), d.get("dram__bytes_write.sum", 0.0))
+        for i, d in sorted(per.items())]
 with open(os.path.join(OUT, f"{tag}_launch_list.csv"), "w") as fh:
-    fh.write("id,kernel,grid,block,us\n")
+    fh.write("id,kernel,grid,block,us,dram_read_bytes,dram_write_bytes\n")
     for r in rows:
-        fh.write(f'{r[0]},"{r[1]}","{r[2]}","{r[3]}",{r[4]:.3f}\n')
+        fh.write(f'{r[0]},"{r[1]}","{r[2]}","{r[3]}",{r[4]:.3f},{r[5]:.0f},{r[6]:.0f}\n')
 tot = sum(r[4] for r in rows)
+traffic = sum(r[5] + r[6] for r in rows)
 agg = {}
 for r in rows:
-    agg.setdefault(r[1], [0, 0.0]); agg[r[1]][0] += 1; agg[r[1]][1] += r[4]
-md = [f"# {tag}: launch list of one HiFi-GAN V1 forward (fp16, B=16, T=759), ncu gpu__time_duration.sum\n",
-      "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:\"conv_tc|conv_post|cf_to_cl|lr_\" -s 79 -c 80 --csv python tools/ncu_forward.py`",
+    a = agg.setdefault(r[1], [0, 0.0, 0.0]); a[0] += 1; a[1] += r[4]; a[2] += r[5] + r[6]
+md = [f"# {tag}: launch list of one HiFi-GAN V1 forward (fp16, B=16, T=759, no padding trim), ncu\n",
+      "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+      "-k 'regex:conv_tc|unit_tc|unit64_tc|conv_post|cf_to_cl' -s 52 -c 52 --csv python tools/ncu_forward.py`",
       "(per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes)\n",
-      "| kernel | launches | total us | share |", "|---|---|---|---|"]
-for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    md.append(f"| `{k}` | {n} | {us:.1f} | {100 * us / tot:.1f}% |")
-md.append(f"\nTotal {tot:.1f} us over {len(rows)} launches.\n")
+      "| kernel | launches | total us | share | DRAM read+write MB |", "|---|---|---|---|---|"]
+for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    md.append(f"| `{k}` | {n} | {us:.1f} | {100 * us / tot:.1f}% | {by / 1e6:.1f} |")
+md.append(f"\nTotal {tot:.1f} us over {len(rows)} launches; DRAM traffic of the launch set {traffic / 1e9:.3f} GB.\n")
+json.dump({"launches": len(rows), "dram_bytes_per_forward": traffic, "ncu_us_per_forward": tot,
+           "workload": "HiFi-GAN V1 forward, fp16 operands, B=16, T=759 frames, no padding trim"},
+          open(os.path.join(OUT, f"{tag}_traffic.json"), "w"))
 
 # 2. full captures
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum", "sm__cycles_elapsed.max",
         "sm__inst_executed_pipe_tensor.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-for rep, what in (("prof_stage1_k11", "stage 1 (128 ch) k=11: conv1 (operand copy only) then conv2 (residual epilogue) -- tensor-bound layers"),
-                  ("prof_stage3_k3", "stage 3 (32 ch) k=3: conv1 then conv2 -- HBM-bound layers")):
+for rep, what in (("prof_unit_c128_k11", "stage 1 (128 ch) fused unit k=11, d=1 (`unit_tc_kernel`) -- tensor / L2-weight-stream bound"),
+                  ("prof_unit64_c64_k11", "stage 2 (64 ch) fused unit k=11, d=1 (`unit64_tc_kernel`, M=64, resident weights)"),
+                  ("prof_unit64_c32_k3", "stage 3 (32 ch) fused unit k=3, d=1 (`unit64_tc_kernel`) -- HBM-bound"),
+                  ("prof_conv_c256_k11", "stage 0 (256 ch) k=11: conv1 then conv2 (`conv_tc_kernel`)")):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -44,12 +60,31 @@ for rep, what in (("prof_stage1_k11", "stage 1 (128 ch) k=11: conv1 (operand cop
     hdr, units = rr[0], rr[1]
     idx = {h: i for i, h in enumerate(hdr)}
     md.append(f"## ncu --set full: {what}\n")
-    md.append(f"Report: `{rep}.ncu-rep` (scratch, not committed); command: `ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s <n> -c 2 python tools/ncu_forward.py`\n")
-    md.append("| metric | unit | launch 1 | launch 2 |"); md.append("|---|---|---|---|")
+    md.append(f"Report: `{rep}.ncu-rep` (scratch, not committed); command in `tools/gpu_full.sh`\n")
+    nl = len(rr) - 2
+    md.append("| metric | unit | " + " | ".join(f"launch {i + 1}" for i in range(nl)) + " |"); md.append("|---|---|" + "---|" * nl)
     for w in want:
         if w in idx:
-            vals = [r[idx[w]] for r in rr[2:4]]
+            vals = [r[idx[w]] for r in rr[2:2 + nl]]
             md.append(f"| {w} | {units[idx[w]]} | " + " | ".join(vals) + " |")
+    # warp-stall distribution from the source page
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    hdr2, tots, samples = None, {}, 0
+    for r in csv.reader(src.splitlines()):
+        if r and r[0] == "Address":
+            if hdr2 is not None: break          # first kernel only
+            hdr2 = r; ix = {h: i for i, h in enumerate(hdr2)}; continue
+        if hdr2 is None or len(r) < len(hdr2): continue
+        try: n = int(r[ix["# Samples"]])
+        except ValueError: continue
+        samples += n
+        for h in hdr2:
+            if h.startswith("stall_") and "Not Issued" not in h:
+                try: tots[h] = tots.get(h, 0) + int(r[ix[h]])
+                except ValueError: pass
+    if samples:
+        top = sorted(tots.items(), key=lambda kv: -kv[1])[:6]
+        md.append("\nWarp-state samples (launch 1): " + ", ".join(f"{h} {100 * v / samples:.1f}%" for h, v in top) + "\n")
     md.append("")
 open(os.path.join(OUT, f"{tag}_ncu_summary.md"), "w").write("\n".join(md))
 
