@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--ref-utts", type=int, default=2, help="utterances per step for the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN) timing of the module tree")
     ap.add_argument("--no-trim", action="store_true", help="process the padded tail of short utterances too")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -291,6 +292,30 @@ def main():
         torch.cuda.synchronize(dev)
         untrimmed_ms = sum(a_.elapsed_time(b_) for a_, b_ in uev) / len(uev)
 
+        # context (SURVEY 8d "the real bar"): the same nn.Module tree run eagerly by PyTorch/cuDNN on this GPU -- what the
+        # reference's own modules do on a B200.  This is the shells' autograd/eager path (hifigan.py:_forward_eager),
+        # outside every timed region above; rank 0 only.
+        eager = None
+        if rank == 0 and not args.no_eager_baseline:
+            eager = {}
+            old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            for name, tf32 in (("tf32", True), ("fp32", False)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                for _ in range(2):
+                    gen._forward_eager(mel_full)
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+                for a_, b_ in ev:
+                    a_.record()
+                    gen._forward_eager(mel_full)
+                    b_.record()
+                torch.cuda.synchronize(dev)
+                ms = sorted(a_.elapsed_time(b_) for a_, b_ in ev)[1]
+                eager[f"generator_ms_{name}"] = ms
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+            eager["note"] = ("PyTorch eager (cuDNN) forward of the same module tree, padded batch, no trim; compare with "
+                             "config.generator_ms_untrimmed")
+
         # ---- end-to-end through the public API with host buffers (H2D + D2H inside) -------------
         e2e_ms = []
         barrier()
@@ -353,6 +378,7 @@ def main():
                 "frames_needed_for_roofline": needed_frames,
                 "generator_ms_untrimmed": untrimmed_ms,
                 "untrimmed_generator_tflops": padded_frames * FLOP_PER_FRAME_V1 / (untrimmed_ms * 1e-3) / 1e12,
+                "torch_eager_gpu": eager,
             },
             "clocks": clocks.summary(),
             "e2e": {"value": audio_all * args.steps / (e2e_ms_all * 1e-3), "unit": "audio_s/s",

@@ -210,3 +210,27 @@ def test_baseline_config_shapes_fp16_vs_fp32_kernels(B, T):
     assert rel_l2(y, ref) <= BF16_REL and max_abs(y, ref) <= BF16_MAXABS
     assert max_abs(y[-1:], y_last) < 1e-6
     assert bool(torch.isfinite(y).all())
+
+
+@pytest.mark.parametrize("T", [37, 112, 5])
+def test_fused_narrow_units_odd_lengths_vs_oracle(T):
+    """64- and 32-channel fused units (unit64 kernel) on stage lengths that are odd / not multiples of the
+    4-sample packing, the 16-column epilogue groups or the 112-position tile: T*3 and T*15 samples."""
+    kw = dict(in_channels=16, channels=128, upsample_scales=[3, 5], upsample_kernel_sizes=[6, 10])
+    torch.manual_seed(11)
+    m = vtts_b200.HiFiGAN(**kw)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.precision = "fp16"
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(T)
+    c = torch.randn(3, 16, T, generator=g)
+    ref = restate.hifigan_forward(sd, c, upsample_scales=(3, 5))
+    with torch.no_grad():
+        y = m(c.to(DEV))
+        lens = torch.tensor([T, max(1, T // 3), max(1, T - 2)], device=DEV)
+        yt = m.forward_trimmed(c.to(DEV), lens)
+    assert y.shape == ref.shape
+    assert rel_l2(y, ref) <= BF16_REL and max_abs(y, ref) <= BF16_MAXABS, (rel_l2(y, ref), max_abs(y, ref))
+    for b in range(3):
+        n = int(lens[b]) * 15
+        assert torch.equal(y[b, :, :n], yt[b, :, :n])
