@@ -78,6 +78,18 @@ int vtts_gauss_upsample(const float *hs, const int64_t *ds, const unsigned char 
                         float delta, vtts_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * vits2 monotonic duration path -- replaces models/gan_tts/vits2/utils.py:111-126 (generate_path) and the
+ * attn matmuls at models/gan_tts/vits2/generator.py:256-259.
+ * duration (B,t_x) fp32 (the [b,1,t_x] tensor, integer valued at the call site: w_ceil), mask (B,t_y,t_x) fp32 or NULL
+ * (the [b,1,t_y,t_x] attn_mask), path (B,t_y,t_x) fp32.
+ * vtts_path_expand computes matmul(path, x^T)^T without materialising the path: x (B,D,t_x) -> out (B,D,t_y).
+ * ---------------------------------------------------------------------------------------- */
+int vtts_path_generate(const float *duration, const float *mask, float *path, int B, int t_y, int t_x,
+                       vtts_stream_t stream);
+int vtts_path_expand(const float *x, const float *duration, const float *mask, float *out, int B, int D, int t_y,
+                     int t_x, vtts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * HiFi-GAN generator -- replaces models/gan_tts/hifigan/generator.py:132-156
  * (HiFiGAN.forward), layers.py:83-98 (ResidualBlock.forward) and the vits2 skin
  * models/gan_tts/vits2/layers.py:159-177 (Generator.forward), sublayers.py:293-303,341-349.

@@ -125,3 +125,11 @@ def load_gaussian_upsampling():
     import sys as _sys
 
     return _sys.modules["models.tts.fastspeech2.layers"].GaussianUpsampling
+
+
+def load_vits2_utils():
+    """Return the reference module ``models/gan_tts/vits2/utils.py`` (generate_path :111-126, sequence_mask :104-108)."""
+    _placeholder("models", os.path.join(REF_ROOT, "models"))
+    _placeholder("models.gan_tts", os.path.join(REF_ROOT, "models/gan_tts"))
+    _placeholder("models.gan_tts.vits2", os.path.join(REF_ROOT, "models/gan_tts/vits2"))
+    return _load_file("models.gan_tts.vits2.utils", "models/gan_tts/vits2/utils.py")

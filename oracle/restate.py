@@ -308,3 +308,30 @@ def gaussian_upsampling(hs: torch.Tensor, ds: torch.Tensor, h_masks: Optional[to
         energy = energy.masked_fill(~(d_masks.unsqueeze(1).repeat(1, T_feats, 1)), -float("inf"))
     p_attn = torch.softmax(energy, dim=2)                                   # layers.py:516
     return torch.matmul(p_attn, hs.float())                                 # layers.py:517
+
+
+# --------------------------------------------------------------------------------------------
+# vits2 monotonic duration path  (models/gan_tts/vits2/utils.py:104-126; call site vits2/generator.py:251-259)
+# --------------------------------------------------------------------------------------------
+
+
+def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Restates ``generate_path`` (utils.py:111-126) with explicit index arithmetic.
+
+    duration [b, 1, t_x], mask [b, 1, t_y, t_x] -> path [b, 1, t_y, t_x]:
+    ``path[b,0,y,x] = ((y < cum[b,x]) - (y < cum[b,x-1])) * mask[b,0,y,x]`` with ``cum = cumsum(duration)``
+    (``sequence_mask`` compares an arange of duration's dtype, utils.py:104-108).
+    """
+    b, _, t_y, t_x = mask.shape
+    cum = torch.cumsum(duration, -1).view(b, t_x)                       # utils.py:120-122
+    y = torch.arange(t_y, dtype=cum.dtype).view(1, t_y, 1)
+    below = (y < cum.view(b, 1, t_x)).to(mask.dtype)                    # sequence_mask, transposed to (b, t_y, t_x)
+    prev = torch.zeros_like(below)
+    prev[:, :, 1:] = below[:, :, :-1]                                   # F.pad(path, [[0,0],[1,0],[0,0]])[:, :-1]
+    return (below - prev).unsqueeze(1) * mask                           # utils.py:124-125
+
+
+def expand_by_path(x: torch.Tensor, duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """``torch.matmul(attn.squeeze(1), x.transpose(1, 2)).transpose(1, 2)`` (vits2/generator.py:256-259)."""
+    attn = generate_path(duration, mask)
+    return torch.matmul(attn.squeeze(1), x.transpose(1, 2)).transpose(1, 2)

@@ -173,8 +173,39 @@ def gaussian_cases():
     print("gaussian_cases ok")
 
 
+def path_cases():
+    """vits2 generate_path + the attn matmuls of VITS2.inference (vits2/generator.py:246-259), run on the reference."""
+    U = ref_loader.load_vits2_utils()
+    g = torch.Generator().manual_seed(7)
+    out = {}
+
+    def add(name, w, x_len, d_ch, feats_lengths=None):
+        b, _, t_x = w.shape
+        x_mask = U.sequence_mask(x_len, t_x).unsqueeze(1).to(w.dtype)                    # [b,1,t_x]
+        w = w * x_mask
+        w_ceil = torch.ceil(w)
+        if feats_lengths is None:
+            feats_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()          # generator.py:251
+        y_mask = torch.unsqueeze(U.sequence_mask(feats_lengths, None), 1).to(x_mask.dtype)
+        attn_mask = torch.unsqueeze(x_mask, 2) * torch.unsqueeze(y_mask, -1)
+        attn = U.generate_path(w_ceil, attn_mask)
+        m_p = torch.randn(b, d_ch, t_x, generator=g)
+        m_out = torch.matmul(attn.squeeze(1), m_p.transpose(1, 2)).transpose(1, 2)
+        out.update({f"{name}.w_ceil": w_ceil.numpy(), f"{name}.attn_mask": attn_mask.numpy(), f"{name}.attn": attn.numpy(),
+                    f"{name}.m_p": m_p.numpy(), f"{name}.m_out": m_out.contiguous().numpy()})
+
+    add("basic", torch.rand(3, 1, 13, generator=g) * 4, torch.tensor([13, 9, 5]), 24)
+    add("zeros_inside", torch.tensor([[[0.0, 2.2, 0.0, 0.0, 3.0, 0.4]], [[1.0, 0.0, 0.0, 0.0, 0.0, 5.5]]]), torch.tensor([6, 6]), 7)
+    add("all_zero_row", torch.tensor([[[0.0, 0.0, 0.0]], [[2.0, 1.0, 3.0]]]), torch.tensor([3, 3]), 5)      # clamp_min(…, 1)
+    add("long", torch.rand(4, 1, 120, generator=g) * 9, torch.tensor([120, 77, 40, 101]), 40)
+    add("short_y", torch.rand(2, 1, 10, generator=g) * 5, torch.tensor([10, 10]), 16, feats_lengths=torch.tensor([9, 4]))
+    np.savez_compressed(os.path.join(OUT, "path_cases.npz"), **out)
+    print("path_cases ok")
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs /root/reference"
+    path_cases()
     gaussian_cases()
     lr_cases()
     hifigan_small()

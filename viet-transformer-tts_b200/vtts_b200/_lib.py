@@ -46,6 +46,9 @@ SIGNATURES = {
                                  C.c_int, C.c_void_p, C.c_void_p]),
     "vtts_gauss_upsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "vtts_path_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtts_path_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
     "vtts_gen_create": (C.c_int, [C.POINTER(VttsGenConfig), C.POINTER(C.c_void_p)]),
     "vtts_gen_destroy": (C.c_int, [C.c_void_p]),
     "vtts_gen_num_layers": (C.c_int, [C.c_void_p]),

@@ -12,6 +12,7 @@ Replaced symbols (reference file:line):
   models/tts/fastspeech2/layers.py:410     LengthRegulator      :465 GaussianUpsampling
   models/gan_tts/vits2/layers.py:107       Generator
   models/gan_tts/vits2/sublayers.py:215    ResBlock1      :312 ResBlock2
+  models/gan_tts/vits2/utils.py:111        generate_path (also the name imported into vits2/generator.py:8)
 Every module already imported that holds a reference to one of the original classes (e.g.
 ``from models.gan_tts.hifigan import HiFiGAN`` in text2wav/model.py:5) is patched too.
 """
@@ -28,18 +29,19 @@ _TARGETS = {
     "models.gan_tts.jets.alignments": ("GaussianUpsampling",),
     "models.gan_tts.vits2.layers": ("Generator",),
     "models.gan_tts.vits2.sublayers": ("ResBlock1", "ResBlock2"),
+    "models.gan_tts.vits2.utils": ("generate_path",),
 }
 _saved: Dict[Tuple[str, str], object] = {}
 
 
 def _replacements():
-    from . import gaussian_upsampling, hifigan, length_regulator, vits2
+    from . import gaussian_upsampling, hifigan, length_regulator, vits2, vits2_path
 
     return {
         "HiFiGAN": hifigan.HiFiGAN, "ResidualBlock": hifigan.ResidualBlock,
         "LengthRegulator": length_regulator.LengthRegulator, "Generator": vits2.Generator,
         "GaussianUpsampling": gaussian_upsampling.GaussianUpsampling,
-        "ResBlock1": vits2.ResBlock1, "ResBlock2": vits2.ResBlock2,
+        "ResBlock1": vits2.ResBlock1, "ResBlock2": vits2.ResBlock2, "generate_path": vits2_path.generate_path,
     }
 
 
