@@ -351,8 +351,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_after();
     if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     const uint32_t tmem_base = *tmem_slot;
-    grid_dep_wait();      // everything above overlapped the previous kernel's tail (programmatic dependent launch)
-    grid_dep_launch();
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weight producer never
+    // touches data of the previous kernel, so it does not wait at all and fills its ring early.
+    if (warp != WARP_W) { grid_dep_wait(); grid_dep_launch(); }
 
     if (warp == WARP_ACT) {
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
@@ -808,8 +809,8 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tps = p.tps;
-    grid_dep_wait();      // the prologue above overlapped the previous kernel's tail
-    grid_dep_launch();
+    // the prologue above overlapped the previous kernel's tail; the weight producer (constant data only) does not wait
+    if (warp != EPI_WARPS + 1) { grid_dep_wait(); grid_dep_launch(); }
 
     if (warp == WARP_ACT) {
         if (lane == 0) {
@@ -1361,10 +1362,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             int slot = 0;
             for (int j = u.n_stream; j < p.taps; ++j, ++slot) tma_load_3d(s_wres + (size_t)slot * TAPB, &tm_w1, wres_full, 0, 0, j);
             for (int j = 0; j < u.taps2; ++j, ++slot) tma_load_3d(s_wres + (size_t)slot * TAPB, &tm_w2, wres_full, 0, 0, j);
-        }
-        grid_dep_wait();
-        grid_dep_launch();
-        if (lane == 0) {
+            // (no grid-dependency wait in this warp: weights are constant data)
             if (u.n_stream > 0) {
                 uint32_t s = 0, ph = 0;
                 for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w))
