@@ -326,14 +326,31 @@ def main():
             wav_h, wav_len_h = synth(hs_pin, ds_pin)  # synchronises before returning
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
         barrier()
-        e2e_total = sum(e2e_ms)
+        e2e_sync_total = sum(e2e_ms)
+        # pipelined form (Synthesizer.submit): same per-step host->device inputs and device->host waveform, but the
+        # read-back of step k runs on a copy stream behind the kernels of step k+1.  No L2 flush inside this region
+        # (it cannot be excluded from the clock here); the per-step working set is far larger than L2 anyway.
+        for _ in range(2):
+            synth.submit(hs_pin, ds_pin).result()
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0 = time.perf_counter()
+        pending = None
+        for k in range(args.steps):
+            nxt = synth.submit(hs_pin, ds_pin)
+            if pending is not None:
+                wav_h, wav_len_h = pending.result()
+            pending = nxt
+        wav_h, wav_len_h = pending.result()
+        e2e_total = 1e3 * (time.perf_counter() - t0)
+        barrier()
 
-    t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_total, e2e_sync_total], dtype=torch.float64, device=dev)
     a = torch.tensor([audio_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
-    total_ms_all, e2e_ms_all = t.tolist()
+    total_ms_all, e2e_ms_all, e2e_sync_ms_all = t.tolist()
     audio_all = float(a.item())
 
     if rank == 0:
@@ -384,7 +401,11 @@ def main():
             "e2e": {"value": audio_all * args.steps / (e2e_ms_all * 1e-3), "unit": "audio_s/s",
                     "h2d_bytes_per_step": hs.numel() * 4 + ds.numel() * 8,
                     "d2h_bytes_per_step": int(wav.numel()) * 4 + ds.shape[0] * 8,
-                    "ms_per_step": e2e_ms_all / args.steps},
+                    "ms_per_step": e2e_ms_all / args.steps,
+                    "mode": "Synthesizer.submit(): read-back of step k overlaps the kernels of step k+1; every step's "
+                            "inputs and waveform cross PCIe inside the timed region",
+                    "sync_value": audio_all * args.steps / (e2e_sync_ms_all * 1e-3),
+                    "sync_note": "Synthesizer.__call__(): one blocking call per step (H2D, kernels, D2H, sync)"},
             "gpu_launches": launches_per_step * args.steps * world,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                          "frac": achieved / tc_peak, "traffic": traffic_bytes,

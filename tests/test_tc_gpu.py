@@ -193,6 +193,38 @@ def test_synthesizer_trim_matches_untrimmed_on_valid_audio():
         assert torch.equal(wav_t[b, :, :n], wav_f[b, :, :n])
 
 
+def test_synthesizer_submit_pipeline_matches_blocking_calls():
+    """submit()/result(): three batches in flight order, each result equal to the blocking call's."""
+    m, _ = v1_model("fp16")
+    synth = vtts_b200.Synthesizer(m)
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for B, T in [(3, 12), (2, 25), (4, 7)]:
+        hs = torch.randn(B, T, 96, generator=g).pin_memory()
+        ds = torch.randint(1, 5, (B, T), generator=g)
+        ds[0, T // 2:] = 0
+        batches.append((hs, ds.pin_memory()))
+    want = []
+    for hs, ds in batches:
+        w, l = synth(hs, ds)
+        want.append((w.clone(), l.clone()))
+    got, pending = [], None
+    for hs, ds in batches:
+        nxt = synth.submit(hs, ds)
+        if pending is not None:
+            w, l = pending.result()
+            got.append((w.clone(), l.clone()))
+        pending = nxt
+    w, l = pending.result()
+    got.append((w.clone(), l.clone()))
+    assert pending.done()
+    for (w0, l0), (w1, l1) in zip(want, got):
+        assert torch.equal(l0, l1) and w0.shape == w1.shape
+        for b in range(w0.shape[0]):
+            n = int(l0[b])
+            assert torch.equal(w0[b, :, :n], w1[b, :, :n])
+
+
 @pytest.mark.parametrize("B,T", [(4, 1000), (1, 2000), (64, 100)])
 def test_baseline_config_shapes_fp16_vs_fp32_kernels(B, T):
     """BASELINE.json configs 4/5 corners (long utterances, wide batch): fp16 tensor-core path vs the fp32

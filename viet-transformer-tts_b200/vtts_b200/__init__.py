@@ -11,13 +11,13 @@ from .gaussian_upsampling import GaussianUpsampling
 from .hifigan import HiFiGAN, ResidualBlock
 from .length_regulator import LengthRegulator
 from .sharding import gather_waveforms, plan_shards, shard_batch
-from .synthesis import Synthesizer
+from .synthesis import PendingSynthesis, Synthesizer
 from .vits2 import Generator, ResBlock1, ResBlock2
 from .vits2_path import expand_by_path, generate_path
 
 __all__ = [
     "HiFiGAN", "ResidualBlock", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
-    "Synthesizer", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall", "generate_path",
+    "Synthesizer", "PendingSynthesis", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall", "generate_path",
     "expand_by_path",
 ]
 __version__ = "0.1.0"
