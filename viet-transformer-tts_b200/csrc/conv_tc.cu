@@ -1750,7 +1750,7 @@ __global__ void __launch_bounds__(256)
 conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /* [k][C] */, const float *__restrict__ bias,
                      float *__restrict__ y, int L, int L4, int ksize, float slope, int out_channels, int oc,
                      const long long *__restrict__ lens, int len_margin, int len_rate) {
-    extern __shared__ float s_tile[];  // [(256 + 8)][C + 1] rows = time t0-4 .. t0+259
+    extern __shared__ float s_tile[];  // [C][256 + 8 + 4]: time t0-4 .. t0+259 per channel
     const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;   // h <= 4
     grid_dep_wait();
     grid_dep_launch();
@@ -1760,25 +1760,31 @@ conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /*
         if (t < L) y[((size_t)b * out_channels + oc) * L + t] = 0.f;
         return;
     }
-    constexpr int ROWS = 256 + 8;
+    constexpr int ROWS = 256 + 8, PITCH = ROWS + 4;   // channel-major tile: float4 rows, conflict-free 128-bit stores
     const float *xb = x + (size_t)b * L4 * C * 4;
-    // memory order: (t/4, c, t%4); tile covers t in [t0-4, t0+260)
-    for (int m = threadIdx.x; m < ROWS * C; m += 256) {
-        const int dt = m & 3, c = (m >> 2) % C, r4 = (m >> 2) / C;
-        const int t = t0 - 4 + r4 * 4 + dt;
-        float v = 0.f;
-        if (t >= 0 && t < L) v = lrelu(__ldg(xb + ((size_t)(t >> 2) * C + c) * 4 + dt), slope);
-        s_tile[(r4 * 4 + dt) * (C + 1) + c] = v;
+    // memory order: (t/4, c, t%4); tile covers t in [t0-4, t0+260): one 128-bit load per (t/4, c)
+    for (int m = threadIdx.x; m < (ROWS / 4) * C; m += 256) {
+        const int c = m % C, r4 = m / C;
+        const int tb = t0 - 4 + r4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tb >= 0 && tb < L) {
+            v = __ldg(reinterpret_cast<const float4 *>(xb + ((size_t)(tb >> 2) * C + c) * 4));
+            v.x = lrelu(v.x, slope);
+            v.y = tb + 1 < L ? lrelu(v.y, slope) : 0.f;
+            v.z = tb + 2 < L ? lrelu(v.z, slope) : 0.f;
+            v.w = tb + 3 < L ? lrelu(v.w, slope) : 0.f;
+        }
+        *reinterpret_cast<float4 *>(s_tile + c * PITCH + r4 * 4) = v;
     }
     __syncthreads();
     const int t = t0 + threadIdx.x;
     if (t >= L) return;
     float acc = 0.f;
     for (int k = 0; k < ksize; ++k) {
-        const float *row = s_tile + (threadIdx.x + 4 - h + k) * (C + 1);
+        const float *col = s_tile + (threadIdx.x + 4 - h + k);
         const float *wk = w + k * C;
 #pragma unroll 8
-        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(wk + c), row[c], acc);
+        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(wk + c), col[c * PITCH], acc);
     }
     if (bias) acc += __ldg(bias + oc);
     y[((size_t)b * out_channels + oc) * L + t] = tanhf(acc);
@@ -2154,7 +2160,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         const bool pdl = pdl_enabled() && !prof_enabled();
         dim3 grid((unsigned)ceil_div(L, 256), (unsigned)B);
         if (k > 9) return set_error(VTTS_E_UNSUPPORTED, "conv_post: kernel size %d > 9", k);
-        const size_t smem = (size_t)(256 + 8) * (C + 1) * sizeof(float);
+        const size_t smem = (size_t)C * (256 + 8 + 4) * sizeof(float);
         for (int oc = 0; oc < post.info.cout; ++oc) {
             const float *w_oc = wt + (size_t)oc * k * C;
             const float *bias = post.has_bias ? post.bias : nullptr;
