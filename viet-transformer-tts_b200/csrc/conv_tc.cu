@@ -1777,17 +1777,31 @@ conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /*
         *reinterpret_cast<float4 *>(s_tile + c * PITCH + r4 * 4) = v;
     }
     __syncthreads();
-    const int t = t0 + threadIdx.x;
-    if (t >= L) return;
-    float acc = 0.f;
-    for (int k = 0; k < ksize; ++k) {
-        const float *col = s_tile + (threadIdx.x + 4 - h + k);
-        const float *wk = w + k * C;
-#pragma unroll 8
-        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(wk + c), col[c * PITCH], acc);
+    // 64 threads x 4 consecutive outputs: per channel three 128-bit shared loads (t-4 .. t+7) feed 4 x ksize FMAs
+    // (one load per FMA made this kernel shared-memory bound); the other threads only helped with the tile load
+    if (threadIdx.x >= 64) return;
+    const int tl4 = threadIdx.x * 4;                         // first output of this thread inside the tile
+    if (t0 + tl4 >= L) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+        const float4 *col = reinterpret_cast<const float4 *>(s_tile + c * PITCH + tl4);   // tile index 0 is t0-4
+        const float4 a = col[0], bq = col[1], cq = col[2];
+        const float v[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, cq.x, cq.y, cq.z, cq.w};   // t-4 .. t+7
+#pragma unroll
+        for (int j = -4; j <= 4; ++j) {                      // tap k = j + h reads t + j: static register indices
+            const int k = j + h;
+            if (k >= 0 && k < ksize) {
+                const float wk = __ldg(w + k * C + c);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[o] = fmaf(wk, v[o + 4 + j], acc[o]);
+            }
+        }
     }
-    if (bias) acc += __ldg(bias + oc);
-    y[((size_t)b * out_channels + oc) * L + t] = tanhf(acc);
+    const float bv = bias ? __ldg(bias + oc) : 0.f;
+    float *yo = y + ((size_t)b * out_channels + oc) * L + t0 + tl4;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (t0 + tl4 + o < L) yo[o] = tanhf(acc[o] + bv);
 }
 
 // debug / test layout converters for the time-packed fp32 stream
