@@ -292,6 +292,30 @@ def main():
         torch.cuda.synchronize(dev)
         untrimmed_ms = sum(a_.elapsed_time(b_) for a_, b_ in uev) / len(uev)
 
+        # LengthRegulator alone (HBM-bandwidth class, launch-latency bound at these sizes): kernels only
+        # (max_len given -> no host read), algorithmic bytes = xs + ds read, frames + mel_len written
+        lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a_, b_ in lev:
+            flush.fill_(2)
+            a_.record()
+            lr.forward_with_lengths(hs_d, ds_d, max_len=T_out)
+            b_.record()
+        torch.cuda.synchronize(dev)
+        lr_us = sorted(1e3 * a_.elapsed_time(b_) for a_, b_ in lev)[len(lev) // 2]
+        lr_bytes = hs_d.numel() * 4 + ds_d.numel() * 8 + frames.numel() * 4 + ds_d.shape[0] * 8
+        # single-utterance latency at configs[0] (B=1, T=200 frames = 2.3 s of audio): blocking module call, wall clock
+        mel1 = torch.randn(1, 80, 200, device=dev)
+        for _ in range(3):
+            gen(mel1)
+        torch.cuda.synchronize(dev)
+        lat = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            gen(mel1)
+            torch.cuda.synchronize(dev)
+            lat.append(1e3 * (time.perf_counter() - t0))
+        lat.sort()
+
         # context (SURVEY 8d "the real bar"): the same nn.Module tree run eagerly by PyTorch/cuDNN on this GPU -- what the
         # reference's own modules do on a B200.  This is the shells' autograd/eager path (hifigan.py:_forward_eager),
         # outside every timed region above; rank 0 only.
@@ -396,6 +420,10 @@ def main():
                 "generator_ms_untrimmed": untrimmed_ms,
                 "untrimmed_generator_tflops": padded_frames * FLOP_PER_FRAME_V1 / (untrimmed_ms * 1e-3) / 1e12,
                 "torch_eager_gpu": eager,
+                "length_regulator": {"us": lr_us, "algorithmic_bytes": lr_bytes, "GBps": lr_bytes / (lr_us * 1e-6) / 1e9,
+                                     "note": "kernels only (rowsum + gather), output length supplied; launch-latency bound"},
+                "latency_ms_configs0_b1_t200": {"median": lat[len(lat) // 2], "min": lat[0],
+                                                "note": "HiFiGAN.forward on (1,80,200), blocking, wall clock"},
             },
             "clocks": clocks.summary(),
             "e2e": {"value": audio_all * args.steps / (e2e_ms_all * 1e-3), "unit": "audio_s/s",

@@ -193,6 +193,27 @@ def test_synthesizer_trim_matches_untrimmed_on_valid_audio():
         assert torch.equal(wav_t[b, :, :n], wav_f[b, :, :n])
 
 
+@pytest.mark.parametrize("alpha", [1.0, 1.3, 0.5])
+def test_synthesizer_host_durations_match_device_durations(alpha):
+    """Host-side duration sums (no device->host read) give the same frames/lengths as the module path with device
+    durations, including torch.round half-to-even under alpha (layers.py:446-448)."""
+    m, _ = v1_model("fp16")
+    synth = vtts_b200.Synthesizer(m)
+    g = torch.Generator().manual_seed(31)
+    hs = torch.randn(3, 14, 96, generator=g)
+    ds = torch.randint(0, 6, (3, 14), generator=g)
+    ds[2, 5:] = 0
+    w_h, l_h = synth(hs.pin_memory(), ds.pin_memory(), alpha)            # host durations: sums on the host
+    w_h, l_h = w_h.clone(), l_h.clone()
+    w_d, l_d = synth(hs.to(DEV), ds.to(DEV), alpha)                       # device durations: module path
+    assert torch.equal(l_h, l_d)
+    frames, mel_len = vtts_b200.LengthRegulator().forward_with_lengths(hs.to(DEV), ds.to(DEV), alpha)
+    assert torch.equal(mel_len.cpu() * 256, l_h) and w_h.shape[-1] == frames.shape[1] * 256
+    for b in range(3):
+        n = int(l_h[b])
+        assert torch.equal(w_h[b, :, :n], w_d[b, :, :n])
+
+
 def test_synthesizer_submit_pipeline_matches_blocking_calls():
     """submit()/result(): three batches in flight order, each result equal to the blocking call's."""
     m, _ = v1_model("fp16")
