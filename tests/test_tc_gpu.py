@@ -287,3 +287,23 @@ def test_fused_narrow_units_odd_lengths_vs_oracle(T):
     for b in range(3):
         n = int(lens[b]) * 15
         assert torch.equal(y[b, :, :n], yt[b, :, :n])
+
+
+@pytest.mark.parametrize("resblock,dil", [("1", [[1, 3, 5]] * 3), ("2", [[1, 3]] * 3)])
+def test_vits2_generator_production_widths_fp16_vs_oracle(resblock, dil):
+    """vits2 skin (layers.py:107-186) at the shipped widths: 192-channel latent, 256-channel speaker conditioning,
+    conv_post without bias; ResBlock1 runs the fused unit kernels, ResBlock2 (one conv per unit) the plain conv kernel
+    with the residual epilogue on every width."""
+    torch.manual_seed(3)
+    m = vtts_b200.Generator(192, resblock=resblock, resblock_dilation_sizes=dil, gin_channels=256)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.precision = "fp16"
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 192, 21, generator=g)
+    gc = torch.randn(2, 256, 1, generator=g)
+    ref = restate.vits2_generator_forward(sd, x, gc, resblock=resblock, resblock_dilation_sizes=dil)
+    with torch.no_grad():
+        y = m(x.to(DEV), gc.to(DEV))
+    assert y.shape == ref.shape
+    assert rel_l2(y, ref) <= BF16_REL and max_abs(y, ref) <= BF16_MAXABS, (rel_l2(y, ref), max_abs(y, ref))
