@@ -283,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     uint64_t *acc_full = w_empty + W_STAGES, *acc_empty = acc_full + ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_STAGES);
     int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);   // [MAX_TRIM_BATCH] per-batch tile-start limits (padding trim)
+    int *s_ioff = s_lim + MAX_TRIM_BATCH;                  // [MAX_TRIM_BATCH + 1] first live work item of every batch row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
@@ -299,15 +300,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     // (i0 >= n_pos: loads are zero-filled, the epilogue skips them) that keep the barrier protocol uniform
     // Work items are walked with a mixed-radix counter (m block, time group, batch) advanced by `ncl` with
     // carries: no div/mod on the per-tile path of the single-thread roles.
+    // With the padding trim the item space is COMPACT: only live tiles are numbered (per-batch offsets in s_ioff), so
+    // the static round-robin over CTAs stays balanced however the utterance lengths fall (a strided walk over
+    // (m, tile, batch) with dead tiles skipped left some CTAs with twice the work of others on the short stages).
     struct TileIter {
-        int item, m, g, b, dm, dg, db, mb, gpb;
-        __device__ void init(int first, int step, int m_blocks, int groups) {
-            mb = m_blocks; gpb = groups;
-            item = first; m = first % mb; int r = first / mb; g = r % gpb; b = r / gpb;
+        int item, m, g, b, dm, dg, db, mb, gpb, nb;
+        const int *ioff;
+        __device__ void init(int first, int step, int m_blocks, int groups, const int *offsets = nullptr, int batch = 0) {
+            mb = m_blocks; gpb = groups; ioff = offsets; nb = batch;
+            item = first;
+            if (ioff) { b = 0; locate(); return; }
+            m = first % mb; int r = first / mb; g = r % gpb; b = r / gpb;
             dm = step % mb; r = step / mb; dg = r % gpb; db = r / gpb;
+        }
+        __device__ void locate() {
+            while (b < nb && item >= ioff[b + 1]) ++b;
+            const int r = item - ioff[b];
+            g = r / mb; m = r - g * mb;
         }
         __device__ void next(int step) {
             item += step;
+            if (ioff) { locate(); return; }
             m += dm; int c = 0;
             if (m >= mb) { m -= mb; c = 1; }
             g += dg + c; c = 0;
@@ -346,10 +359,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate + p.len_extra;
             s_lim[i] = lim > 0x7fffffffLL ? 0x7fffffff : (int)lim;
         }
+    if (trimming) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int i = 0; i < p.batch; ++i) {
+                s_ioff[i] = acc;
+                const int lim = s_lim[i] < 0 ? 0 : s_lim[i];
+                int live = (lim + TN - 1) / TN;                       // tiles that start before the limit
+                if (live > p.groups_per_batch) live = p.groups_per_batch;
+                acc += live * p.m_blocks;
+            }
+            s_ioff[p.batch] = acc;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
+    const int n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
+    const int *ioff = trimming ? s_ioff : nullptr;
     const uint32_t tmem_base = *tmem_slot;
     // programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weight producer never
     // touches data of the previous kernel, so it does not wait at all and fills its ring early.
@@ -361,7 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             tma_prefetch_desc(&tm_act);
             uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
             TileIter ti;
-            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch); ti.item < p.total_tiles; ti.next(ncl), ++tl) {
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch); ti.item < n_items; ti.next(ncl), ++tl) {
                 int n0, i0, b;
                 decode(ti, n0, i0, b);
                 (void)n0;
@@ -390,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int tps = p.tps;                               // taps per stage (the box depth of tm_w)
             const size_t stage_bytes = (size_t)W_BYTES * tps;
             TileIter ti;
-            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch); ti.item < p.total_tiles; ti.next(ncl), ++tl) {
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch); ti.item < n_items; ti.next(ncl), ++tl) {
                 int n0, i0w, bw;
                 decode(ti, n0, i0w, bw);
                 if (!tile_live(i0w, bw)) continue;
@@ -431,7 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int tps = p.tps;
             const uint64_t a_stage_step = A_STAGE_STEP * (uint64_t)tps;
             TileIter ti;
-            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch); ti.item < p.total_tiles; ti.next(ncl)) {
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch); ti.item < n_items; ti.next(ncl)) {
                 {
                     int n0m, i0m, bm;
                     decode(ti, n0m, i0m, bm);
@@ -539,17 +568,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
         };
         TileIter ti, tnext;
-        ti.init(cid, ncl, p.m_blocks, p.groups_per_batch);
+        ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch);
         tnext = ti;
-        if (cid < p.total_tiles) prefetch_tile(ti);
+        if (cid < n_items) prefetch_tile(ti);
         // with a single m block and no per-batch bias the thread's bias never changes: load it once
         const bool bias_fixed = p.m_blocks == 1 && p.bias_b == nullptr;
         float bias_const = 0.f;
         if (bias_fixed && p.bias && r_in_copy < p.n_total) bias_const = __ldg(p.bias + (r_in_copy % p.cout));
         uint32_t tl = 0;                                    // counts PROCESSED tiles (accumulator ring)
-        for (; ti.item < p.total_tiles; ti.next(ncl)) {
+        for (; ti.item < n_items; ti.next(ncl)) {
             tnext.next(ncl);
-            if (tnext.item < p.total_tiles) prefetch_tile(tnext);
+            if (tnext.item < n_items) prefetch_tile(tnext);
             if (quarter >= p.epi_quarters) continue;        // this warp's TMEM lanes never hold real rows: prefetch duty only
             int n0, i0, b;
             decode(ti, n0, i0, b);
@@ -630,7 +659,7 @@ struct TcLaunch {
 
 static size_t tc_smem_bytes(int rowb, int act_stages, int w_stages) {
     return (size_t)act_stages * ACT_ROWS * rowb + (size_t)w_stages * TM * rowb +
-           (size_t)(2 * act_stages + 2 * w_stages + 2 * ACC_STAGES) * 8 + 16 + MAX_TRIM_BATCH * sizeof(int);
+           (size_t)(2 * act_stages + 2 * w_stages + 2 * ACC_STAGES) * 8 + 16 + (2 * MAX_TRIM_BATCH + 1) * sizeof(int);
 }
 
 static bool tc_cluster_enabled() {
@@ -775,6 +804,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     uint64_t *accA_full = w_empty + W_STAGES, *xt_full = accA_full + 1, *accB_full = xt_full + 1, *accB_empty = accB_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 1);
     int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
+    int *s_ioff = s_lim + MAX_TRIM_BATCH;          // [MAX_TRIM_BATCH + 1] first live tile index of every batch row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
@@ -785,10 +815,19 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int ncta = (int)gridDim.x;
     const int n_epi = EPI_WARPS / 2;                      // warps per epilogue group (operand / output)
 
-    // work items: (time tile of UN2 outputs, batch); m_blocks == 1
-    auto tile_i0 = [&](int item, int &i0, int &b) { b = item / p.t_tiles; i0 = (item - b * p.t_tiles) * UN2; };
+    // work items: (time tile of UN2 outputs, batch); m_blocks == 1.  With the padding trim only LIVE tiles are numbered
+    // (per-batch offsets in s_ioff, binary search per tile), so the round-robin over CTAs stays balanced.
     const bool trimming = p.lens != nullptr;
-    auto tile_live = [&](int i0, int b) -> bool { return !trimming || i0 < s_lim[b]; };
+    auto tile_i0 = [&](int item, int &i0, int &b) {
+        if (!trimming) { b = item / p.t_tiles; i0 = (item - b * p.t_tiles) * UN2; return; }
+        int lo = 0, hi = p.batch - 1;                      // last b with s_ioff[b] <= item
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_ioff[mid] <= item) lo = mid; else hi = mid - 1;
+        }
+        b = lo; i0 = (item - s_ioff[lo]) * UN2;
+    };
+    auto tile_live = [&](int, int) -> bool { return true; };   // every numbered tile is live
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
@@ -804,11 +843,25 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate + p.len_extra;
             s_lim[i] = lim > 0x7fffffffLL ? 0x7fffffff : (int)lim;
         }
+    if (trimming) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int i = 0; i < p.batch; ++i) {
+                s_ioff[i] = acc;
+                const int lim = s_lim[i] < 0 ? 0 : s_lim[i];
+                int live = (lim + UN2 - 1) / UN2;
+                acc += live > p.t_tiles ? p.t_tiles : live;
+            }
+            s_ioff[p.batch] = acc;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tps = p.tps;
+    const int n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
     // the prologue above overlapped the previous kernel's tail; the weight producer (constant data only) does not wait
     if (warp != EPI_WARPS + 1) { grid_dep_wait(); grid_dep_launch(); }
 
@@ -816,7 +869,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
             uint32_t s = 0, ph = 0;
-            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+            for (int item = blockIdx.x; item < n_items; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
@@ -836,7 +889,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             tma_prefetch_desc(&tm_w2);
             uint32_t s = 0, ph = 0;
             const size_t stage_bytes = (size_t)W_BYTES * tps;
-            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+            for (int item = blockIdx.x; item < n_items; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
@@ -886,7 +939,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             sw = sn; wph = pn;
             if (sn == 0) adesc = adesc_first;
         };
-        for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+        for (int item = blockIdx.x; item < n_items; item += ncta) {
             {
                 int i0, b;
                 tile_i0(item, i0, b);
@@ -959,7 +1012,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const uint32_t cblk = (uint32_t)((chbase % CH) / 8 + (lane >> 3));   // 16-byte chunk of matrix lane/8
             const int mrow = lane & 7;                               // row of that matrix this thread addresses
             const uint32_t t_lo = tmem_base + ((uint32_t)(quarter * 32) << 16), t_hi = t_lo + (16u << 16);
-            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+            for (int item = blockIdx.x; item < n_items; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
@@ -1015,15 +1068,15 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
             const float bias2 = (row_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
             const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
-            for (int item = blockIdx.x; item < p.total_tiles; item += ncta) {
+            for (int item = blockIdx.x; item < n_items; item += ncta) {
                 int i0, b;
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
                 {   // L2 prefetch of the fp32 streams the next live tile reads (residual, running MRF sum): in the
                     // time-packed layout a tile's rows are one contiguous block of (positions / 4) * C * 16 bytes
                     int nx = item + ncta, i0n = 0, bn = 0;
-                    for (; nx < p.total_tiles; nx += ncta) { tile_i0(nx, i0n, bn); if (tile_live(i0n, bn)) break; }
-                    if (nx < p.total_tiles && (R || Cc)) {
+                    for (; nx < n_items; nx += ncta) { tile_i0(nx, i0n, bn); if (tile_live(i0n, bn)) break; }
+                    if (nx < n_items && (R || Cc)) {
                         const int rows4 = min(UN2 / 4, p.L4 - i0n / 4);
                         const long long off = ((long long)bn * p.L4 + i0n / 4) * p.cout * 4;
                         const int n_lines = rows4 * p.cout / 8;                 // 128-byte lines
@@ -1134,7 +1187,7 @@ static int unit_prepare(TcUnitLaunch &L, int fmt, const uint16_t *act, int B, in
     else { p.act_stages = 2; p.w_stages = 4; }                     // 80 + 64 + 64 KB
     L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.xt_chunks = p.chunks;
     L.smem = (size_t)p.act_stages * ACT_ROWS * rowb + (size_t)p.w_stages * p.tps * TM * rowb + (size_t)p.chunks * TN * rowb +
-             (size_t)(2 * p.act_stages + 2 * p.w_stages + 4) * 8 + 16 + MAX_TRIM_BATCH * sizeof(int);
+             (size_t)(2 * p.act_stages + 2 * p.w_stages + 4) * 8 + 16 + (2 * MAX_TRIM_BATCH + 1) * sizeof(int);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc unit: %zu B shared memory", L.smem);
     const int sms = tc_num_sms();
     L.grid = dim3((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
@@ -1280,6 +1333,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     uint64_t *accA_full = wres_full + 1, *xt_full = accA_full + 2, *accB_full = xt_full + 2, *accB_empty = accB_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 2);
     int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
+    int *s_ioff = s_lim + MAX_TRIM_BATCH;          // [MAX_TRIM_BATCH + 1] first live tile index of every batch row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
@@ -1289,21 +1343,26 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     const int ncta = (int)gridDim.x;
     constexpr int N_GRP = EPI_WARPS / 2;          // warps per epilogue group
 
-    // work items: (time tile of VN_B outputs, batch).  Every role walks the same list of LIVE items (tiles that start
-    // before the utterance's trim limit); the walk is incremental - no division on the MMA issuers' path.
+    // work items: (time tile of VN_B outputs, batch).  With the padding trim only LIVE tiles are numbered (per-batch
+    // offsets in s_ioff), so the round-robin over CTAs is balanced; every role walks the same list incrementally - no
+    // division on the MMA issuers' path.
     const bool trimming = p.lens != nullptr;
     struct Walk { int item, t, b; };
-    auto walk_fix = [&](Walk &w) {                // normalise (t, b) and skip dead tiles
-        for (;;) {
-            if (w.t >= p.t_tiles) {
-                if (p.t_tiles >= ncta) { w.t -= p.t_tiles; ++w.b; }
-                else { w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; }
-            }
-            if (w.item >= p.total_tiles || !trimming || w.t * VN_B < s_lim[w.b]) return;
-            w.item += ncta; w.t += ncta;
+    auto walk_fix = [&](Walk &w) {                // locate (t, b) of w.item
+        if (trimming) {
+            while (w.b < p.batch && w.item >= s_ioff[w.b + 1]) ++w.b;
+            w.t = w.item - s_ioff[w.b];
+        } else if (w.t >= p.t_tiles) {
+            if (p.t_tiles >= ncta) { w.t -= p.t_tiles; ++w.b; }
+            else { w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; }
         }
     };
-    auto walk_begin = [&]() { Walk w; w.item = (int)blockIdx.x; w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; walk_fix(w); return w; };
+    auto walk_begin = [&]() {
+        Walk w; w.item = (int)blockIdx.x;
+        if (trimming) { w.b = 0; w.t = 0; } else { w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; }
+        walk_fix(w);
+        return w;
+    };
     auto walk_next = [&](Walk &w) { w.item += ncta; w.t += ncta; walk_fix(w); };
 
     if (threadIdx.x == 0) {
@@ -1323,10 +1382,24 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate + p.len_extra;
             s_lim[i] = lim > 0x7fffffffLL ? 0x7fffffff : (int)lim;
         }
+    if (trimming) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int i = 0; i < p.batch; ++i) {
+                s_ioff[i] = acc;
+                const int lim = s_lim[i] < 0 ? 0 : s_lim[i];
+                int live = (lim + VN_B - 1) / VN_B;
+                acc += live > p.t_tiles ? p.t_tiles : live;
+            }
+            s_ioff[p.batch] = acc;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
     // programmatic dependent launch: the prologue above - and the resident weight loads below, which do not depend on
     // the previous kernel - overlap that kernel's tail; everything else waits for it here
     if (warp != WARP_W) { grid_dep_wait(); grid_dep_launch(); }
@@ -1335,7 +1408,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         if (lane == 0) {
             tma_prefetch_desc(&tm_act);
             uint32_t s = 0, ph = 0;
-            for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w)) {
+            for (Walk w = walk_begin(); w.item < n_items; walk_next(w)) {
                 const int i0 = w.t * VN_B, b = w.b;
                 {   // the fp32 streams the output epilogue of this tile will read (residual, running MRF sum) are one
                     // contiguous block in the time-packed layout: pull it into L2 now, several tiles ahead of its use
@@ -1365,7 +1438,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             // (no grid-dependency wait in this warp: weights are constant data)
             if (u.n_stream > 0) {
                 uint32_t s = 0, ph = 0;
-                for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w))
+                for (Walk w = walk_begin(); w.item < n_items; walk_next(w))
                     for (int j = 0; j < u.n_stream; ++j) {
                         mbar_wait(&w_empty[s], ph ^ 1u);
                         mbar_arrive_expect_tx(&w_full[s], (uint32_t)TAPB);
@@ -1393,7 +1466,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 const uint64_t w1res_desc = wres_desc - (uint64_t)u.n_stream * TAP16;   // resident conv1 tap j at + j * TAP16
                 const int n_stream = u.n_stream, taps1 = p.taps;
                 uint32_t sa = 0, aph = 0, sw = 0, wph = 0, tl = 0;
-                for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+                for (Walk w = walk_begin(); w.item < n_items; walk_next(w), ++tl) {
                     VTTS_TRACE(0);
                     // A[tl & 1] is free once the operand epilogue of tile tl-2 has read it
                     mbar_wait(&xt_full[tl & 1u], ((tl >> 1) & 1u) ^ 1u);
@@ -1440,7 +1513,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 const uint64_t w2_desc = wres_desc + (uint64_t)(p.taps - u.n_stream) * TAP16;
                 const int taps2 = u.taps2;
                 uint32_t tl = 0;
-                for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+                for (Walk w = walk_begin(); w.item < n_items; walk_next(w), ++tl) {
                     mbar_wait(&xt_full[tl & 1u], (tl >> 1) & 1u);     // operand epilogue wrote xt[tl & 1]
                     VTTS_TRACE(2);
                     mbar_wait(&accB_empty[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // output epilogue of tile tl-2 drained B[tl & 1]
@@ -1482,7 +1555,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const uint32_t xt_base = smem_u32(s_xt);
             const uint32_t cblk = (uint32_t)(chb / 8 + ((lane >> 3) & 1));   // 16-byte chunk written by matrix lane/8
             const int mrow = (lane & 7) + 8 * (lane >> 4);                   // row (position) this thread addresses
-            for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+            for (Walk w = walk_begin(); w.item < n_items; walk_next(w), ++tl) {
                 const int i0 = w.t * VN_B;
                 mbar_wait_relaxed(&accA_full[tl & 1u], (tl >> 1) & 1u);
                 if (ew == 0 && lane == 0) VTTS_TRACE(5);
@@ -1528,7 +1601,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const int pg = (lane & 3) >> 1;                           // which group of 4 positions inside 8 columns
             const float bias2 = p.bias ? __ldg(p.bias + ch) : 0.f;
             const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
-            for (Walk w = walk_begin(); w.item < p.total_tiles; walk_next(w), ++tl) {
+            for (Walk w = walk_begin(); w.item < n_items; walk_next(w), ++tl) {
                 const int i0 = w.t * VN_B, b = w.b;
                 auto group_fast = [&](int ibase) { return MODE != EPI_GENERIC && ibase + 16 <= n_valid; };
                 auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + ((ibase >> 2) + pg)) * p.cout + ch) * 4; };
@@ -1641,7 +1714,7 @@ static bool tc_unit64_enabled() {
 static bool unit64_plan(int C, int k1, int k2, int &act_stages, int &w_stages, int &n_stream, int &n_res, size_t &smem) {
     const int rowb = C * 2;
     const size_t tapb = (size_t)V_M * rowb, actb = (size_t)V_ACT_ROWS * rowb, xtb = (size_t)2 * VN_A * rowb;
-    const size_t fixed = xtb + 512 + MAX_TRIM_BATCH * sizeof(int);
+    const size_t fixed = xtb + 512 + (2 * MAX_TRIM_BATCH + 1) * sizeof(int);
     const size_t avail = 227 * 1024;
     const int total = k1 + k2;
     for (act_stages = 4; act_stages >= 2; --act_stages) {
