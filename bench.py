@@ -388,7 +388,9 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         gen_avg_ms = sum(gen_ms) / len(gen_ms)
         margin = gen.TRIM_MARGIN_FRAMES
-        needed_frames = int(torch.clamp(ds.sum(1) + margin, max=T_out).sum()) if trim else padded_frames
+        # algorithmic work of the trimmed step = the valid frames only (the few look-ahead frames per utterance that
+        # the kernels still compute behind mel_len are overhead, not counted)
+        needed_frames = valid_frames if trim else padded_frames
         flops = needed_frames * FLOP_PER_FRAME_V1
         achieved = flops / (gen_avg_ms * 1e-3) / 1e12
         # DRAM bytes of the same launch set: ncu launch list of the untrimmed forward at this shape (profiles/), scaled by
@@ -414,8 +416,8 @@ def main():
                 "valid_mel_frames": valid_frames, "l2": "256 MiB flush buffer written between timed steps; "
                 "per-step activation working set also exceeds the 126 MB L2",
                 "value_counts": "valid (unpadded) audio only",
-                "padding_trim": (f"on: generator tiles beyond mel_len+{margin} frames skipped (valid samples bit-identical, "
-                                 "tests/test_tc_gpu.py)" if trim else "off"),
+                "padding_trim": (f"on: generator tiles beyond mel_len + per-layer receptive-field margin (<= {margin} frames) "
+                                 "skipped (valid samples bit-identical, tests/test_tc_gpu.py)" if trim else "off"),
                 "frames_needed_for_roofline": needed_frames,
                 "generator_ms_untrimmed": untrimmed_ms,
                 "untrimmed_generator_tflops": padded_frames * FLOP_PER_FRAME_V1 / (untrimmed_ms * 1e-3) / 1e12,

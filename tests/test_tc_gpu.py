@@ -177,6 +177,29 @@ def test_padding_trim_leaves_valid_samples_bit_identical():
             assert torch.all(trimmed[b, :, far:] == 0), b
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_padding_trim_random_lengths_bit_identical_and_zero_padded(seed):
+    """Per-layer trim margins follow the receptive field: every valid sample stays bit-identical for arbitrary length
+    mixes (tile-boundary neighbours included) and the trimmed padding of the waveform is zero."""
+    m, _ = v1_model("fp16")
+    g = torch.Generator().manual_seed(100 + seed)
+    B, T = 12, 96
+    c = torch.randn(B, 80, T, generator=g).to(DEV)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    lens[1] = 1
+    lens[2:6] = torch.tensor([30, 31, 32, 33])          # 32 frames * 8 = one 256-position tile of stage 0
+    with torch.no_grad():
+        # poison the workspace so that stale data of a previous pass cannot hide a too-small margin
+        m.forward_trimmed(c * 50.0, torch.full((B,), T, device=DEV))
+        full = m(c)
+        trimmed = m.forward_trimmed(c, lens.to(DEV))
+    for b in range(B):
+        n = int(lens[b]) * 256
+        assert torch.equal(full[b, :, :n], trimmed[b, :, :n]), (b, int(lens[b]))
+        assert float(trimmed[b, :, n:].abs().max()) == 0.0 if n < T * 256 else True
+
+
 def test_synthesizer_trim_matches_untrimmed_on_valid_audio():
     m, _ = v1_model("fp16")
     g = torch.Generator().manual_seed(12)

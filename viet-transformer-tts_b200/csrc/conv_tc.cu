@@ -1827,7 +1827,8 @@ conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /*
     const int b = blockIdx.y, t0 = blockIdx.x * 256, h = (ksize - 1) / 2;   // h <= 4
     grid_dep_wait();
     grid_dep_launch();
-    if (lens != nullptr && (long long)t0 >= (lens[b] + len_margin) * (long long)len_rate) {
+    const long long t_lim = lens != nullptr ? (lens[b] + len_margin) * (long long)len_rate : (long long)L;
+    if ((long long)t0 >= t_lim) {
         // trimmed padding: defined (zero) output, no work
         const int t = t0 + threadIdx.x;
         if (t < L) y[((size_t)b * out_channels + oc) * L + t] = 0.f;
@@ -1874,7 +1875,7 @@ conv_post_tp4_kernel(const float *__restrict__ x, const float *__restrict__ w /*
     float *yo = y + ((size_t)b * out_channels + oc) * L + t0 + tl4;
 #pragma unroll
     for (int o = 0; o < 4; ++o)
-        if (t0 + tl4 + o < L) yo[o] = tanhf(acc[o] + bv);
+        if (t0 + tl4 + o < L) yo[o] = (long long)(t0 + tl4 + o) < t_lim ? tanhf(acc[o] + bv) : 0.f;   // padding: defined zeros
 }
 
 // debug / test layout converters for the time-packed fp32 stream
@@ -2062,7 +2063,7 @@ static void prof_report() {
 }
 // one conv layer on the tensor cores
 static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, int B, int L_in, int L_out, TcConvParams p,
-                    cudaStream_t st, int in_rate = 0) {
+                    cudaStream_t st, int in_rate = 0, int margin = -1) {
     const bool transposed = l.info.kind == 1;
     const int s = transposed ? l.stride : 1;
     p.bias = l.has_bias ? l.bias : nullptr;
@@ -2079,7 +2080,7 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
     // padding trim: positions of this GEMM run at `in_rate` positions per mel frame
     if (h->trim_lens && in_rate > 0) {
         p.lens = (const long long *)h->trim_lens;
-        p.len_margin = h->trim_margin;
+        p.len_margin = margin >= 0 ? margin : h->trim_margin;
         p.len_rate = in_rate;
         p.len_extra = transposed ? p.taps : 0;
     }
@@ -2101,11 +2102,11 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
 }
 // fused (conv1, conv2) unit of a ResidualBlock on the tensor cores
 static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const uint16_t *act, int B, int Lpos,
-                    TcConvParams p, float slope_mid, cudaStream_t st, int rate) {
+                    TcConvParams p, float slope_mid, cudaStream_t st, int rate, int margin = -1) {
     p.bias = l2.has_bias ? l2.bias : nullptr;
     if (h->trim_lens && rate > 0) {
         p.lens = (const long long *)h->trim_lens;
-        p.len_margin = h->trim_margin;
+        p.len_margin = margin >= 0 ? margin : h->trim_margin;
         p.len_rate = rate;
         p.len_extra = 0;
     }
@@ -2151,6 +2152,39 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         if (!exact) h->trim_lens = nullptr;
     }
     const long long *trim_lens = (const long long *)h->trim_lens;
+    // Per-layer trim margins (mel frames beyond mel_len that a layer still computes).  Walking the generator backwards
+    // from the last valid sample: a layer's output is needed E positions past the valid end, its input therefore
+    // E + (taps reach) past it.  The caller's margin (vtts_gen_set_valid_lengths) is an upper bound for every layer.
+    int mg_pre = h->trim_margin, mg_post = h->trim_margin, mg_up[VTTS_MAX_STAGES], mg_mrf[VTTS_MAX_STAGES];
+    for (int i = 0; i < VTTS_MAX_STAGES; ++i) mg_up[i] = mg_mrf[i] = h->trim_margin;
+    if (trim_lens) {
+        auto cap = [&](long long frames) { return (int)(frames < h->trim_margin ? frames : h->trim_margin); };
+        auto frames_of = [](long long ext, long long r) { return (ext + r) / r + 1; };   // ceil((ext + 1) / r) + 1 spare frame
+        long long R[VTTS_MAX_STAGES + 1];
+        R[0] = 1;
+        for (int i = 0; i < cfg.num_upsamples; ++i) R[i + 1] = R[i] * cfg.upsample_scales[i];
+        mg_post = 0;                                                 // output samples beyond mel_len are never needed
+        long long E = (h->layers[h->idx_post].info.ksize - 1) / 2;  // conv_post reads this far past the end
+        for (int i = cfg.num_upsamples - 1; i >= 0; --i) {
+            long long reach = 0;                                     // deepest look-ahead of any ResidualBlock of the stage
+            for (int j = 0; j < cfg.num_blocks; ++j) {
+                long long rj = 0;
+                for (int m = 0; m < cfg.num_dilations[j]; ++m) {
+                    const Layer &c1 = h->layers[h->idx_c1[i][j][m]];
+                    rj += (long long)(c1.info.ksize - 1) / 2 * c1.info.dilation;
+                    if (cfg.use_additional_convs) rj += (h->layers[h->idx_c2[i][j][m]].info.ksize - 1) / 2;
+                }
+                reach = rj > reach ? rj : reach;
+            }
+            const long long E_in = E + reach;                        // every unit of the stage is computed this far
+            mg_mrf[i] = cap(frames_of(E_in, R[i + 1]));
+            const Layer &u = h->layers[h->idx_up[i]];
+            const long long in_ext = (E_in + u.padding) / u.stride + 1;   // upsample input positions past the end
+            mg_up[i] = cap(frames_of(in_ext, R[i]));
+            E = in_ext;
+        }
+        mg_pre = cap(E + 2);
+    }
     auto dump_f32 = [&](int id, const float *src_cl, int C, int L) -> int {
         if (dump_stage != id || !dump_out) return VTTS_OK;
         h->launch_count++;
@@ -2179,7 +2213,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         p.bias_b = bias_b;
         p.out_a = bf.a_c; p.out_a_ld = cfg.channels; p.slope_out = cfg.lrelu_slope;
         p.out_x = (dump_stage == 0) ? bf.x_cs : nullptr;
-        if ((rc = run_conv(h, fmt, pre, bf.a_in, B, T, T, p, st, rate))) return rc;
+        if ((rc = run_conv(h, fmt, pre, bf.a_in, B, T, T, p, st, rate, mg_pre))) return rc;
         if ((rc = dump_f32(0, bf.x_cs, cfg.channels, T))) return rc;
     }
     const uint16_t *cur_a = bf.a_c;
@@ -2191,7 +2225,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         {   // upsample: fp32 residual stream x_u + bf16 operand a_u = lrelu(x_u)
             TcConvParams p{};
             p.out_x = bf.x_u; p.out_a = bf.a_u; p.out_a_ld = C; p.slope_out = cfg.lrelu_slope;
-            if ((rc = run_conv(h, fmt, u, cur_a, B, L, Lo, p, st, rate))) return rc;
+            if ((rc = run_conv(h, fmt, u, cur_a, B, L, Lo, p, st, rate, mg_up[i]))) return rc;
             rate *= u.stride;
             if ((rc = dump_f32(2 * i + 1, bf.x_u, C, Lo))) return rc;
         }
@@ -2212,7 +2246,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                 if (cfg.use_additional_convs && !fuse) {
                     TcConvParams p1{};  // xt = conv1(lrelu(x)); only its LeakyReLU'd bf16 copy is needed
                     p1.out_a = bf.a_t; p1.out_a_ld = C; p1.slope_out = cfg.lrelu_slope;
-                    if ((rc = run_conv(h, fmt, l1, ya, B, Lo, Lo, p1, st, rate))) return rc;
+                    if ((rc = run_conv(h, fmt, l1, ya, B, Lo, Lo, p1, st, rate, mg_mrf[i]))) return rc;
                     fin = &h->layers[h->idx_c2[i][j][m]];
                     fin_in = bf.a_t;
                 }
@@ -2231,8 +2265,8 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                     p2.out_a = na; p2.out_a_ld = C; p2.slope_out = cfg.lrelu_slope;
                 }
                 if (fuse) {
-                    if ((rc = run_unit(h, fmt, l1, h->layers[h->idx_c2[i][j][m]], ya, B, Lo, p2, cfg.lrelu_slope, st, rate))) return rc;
-                } else if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st, rate))) return rc;
+                    if ((rc = run_unit(h, fmt, l1, h->layers[h->idx_c2[i][j][m]], ya, B, Lo, p2, cfg.lrelu_slope, st, rate, mg_mrf[i]))) return rc;
+                } else if ((rc = run_conv(h, fmt, *fin, fin_in, B, Lo, Lo, p2, st, rate, mg_mrf[i]))) return rc;
                 yx = nx; ya = na;
             }
         }
@@ -2256,7 +2290,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         if (smem > 48 * 1024)                                                                                 \
             VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tp4_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         VTTS_CHECK_CUDA(launch_kernel_ex(conv_post_tp4_kernel<CC>, grid, dim3(256), smem, st, pdl, 1u, (const float *)bf.x_cs, w_oc, bias, wav, L, \
-                                         (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc, trim_lens, h->trim_margin, rate)); \
+                                         (L + 3) / 4, k, cfg.final_lrelu_slope, post.info.cout, oc, trim_lens, mg_post, rate)); \
     } while (0)
             if (C == 32) VTTS_POST(32);
             else if (C == 64) VTTS_POST(64);
