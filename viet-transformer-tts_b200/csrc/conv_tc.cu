@@ -78,7 +78,7 @@ constexpr int TN = 256;            // time positions per tile (UMMA N, TMEM colu
 constexpr int TM = 128;            // output rows per tile (UMMA M, TMEM lanes)
 constexpr int HALO_MAX = 64;       // (k-1)*d <= 64
 constexpr int ACT_ROWS = TN + HALO_MAX;
-constexpr int BOX_ROWS = 64;       // activation TMA box height
+constexpr int BOX_ROWS = 16;       // activation TMA box height (small boxes: the tile is fetched to the nearest 16 rows)
 constexpr int ACC_STAGES = 2;      // TMEM accumulators
 constexpr int W_PRODUCERS = 1;     // weight-producer warps (each owns the stages == its index mod 4)
 constexpr int PRODUCER_WARPS = 2 + W_PRODUCERS;  // activation producer, weight producers, MMA issuer
