@@ -315,6 +315,17 @@ def main():
             torch.cuda.synchronize(dev)
             lat.append(1e3 * (time.perf_counter() - t0))
         lat.sort()
+        gf = gen.graphed(mel1)                    # the same forward replayed from a CUDA graph (no per-launch host cost)
+        for _ in range(3):
+            gf(mel1)
+        torch.cuda.synchronize(dev)
+        lat_g = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            gf(mel1)
+            torch.cuda.synchronize(dev)
+            lat_g.append(1e3 * (time.perf_counter() - t0))
+        lat_g.sort()
 
         # context (SURVEY 8d "the real bar"): the same nn.Module tree run eagerly by PyTorch/cuDNN on this GPU -- what the
         # reference's own modules do on a B200.  This is the shells' autograd/eager path (hifigan.py:_forward_eager),
@@ -425,7 +436,9 @@ def main():
                 "length_regulator": {"us": lr_us, "algorithmic_bytes": lr_bytes, "GBps": lr_bytes / (lr_us * 1e-6) / 1e9,
                                      "note": "kernels only (rowsum + gather), output length supplied; launch-latency bound"},
                 "latency_ms_configs0_b1_t200": {"median": lat[len(lat) // 2], "min": lat[0],
-                                                "note": "HiFiGAN.forward on (1,80,200), blocking, wall clock"},
+                                                "cuda_graph_median": lat_g[len(lat_g) // 2],
+                                                "note": "HiFiGAN.forward on (1,80,200), blocking, wall clock; cuda_graph = "
+                                                        "HiFiGAN.graphed() replay of the same launches"},
             },
             "clocks": clocks.summary(),
             "e2e": {"value": audio_all * args.steps / (e2e_ms_all * 1e-3), "unit": "audio_s/s",

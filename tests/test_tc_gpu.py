@@ -330,3 +330,25 @@ def test_vits2_generator_production_widths_fp16_vs_oracle(resblock, dil):
         y = m(x.to(DEV), gc.to(DEV))
     assert y.shape == ref.shape
     assert rel_l2(y, ref) <= BF16_REL and max_abs(y, ref) <= BF16_MAXABS, (rel_l2(y, ref), max_abs(y, ref))
+
+
+def test_graphed_forward_replays_bit_identically_and_tracks_weight_updates():
+    """CUDA-graph capture of the forward (low-latency serving): same bits as the launch path, with and without the
+    padding trim, also after new inputs and after a weight update (re-capture)."""
+    m, _ = v1_model("fp16")
+    g = torch.Generator().manual_seed(8)
+    c1 = torch.randn(2, 80, 33, generator=g).to(DEV)
+    c2 = torch.randn(2, 80, 33, generator=g).to(DEV)
+    lens = torch.tensor([33, 17], device=DEV)
+    with torch.no_grad():
+        gf = m.graphed(c1)
+        gt = m.graphed(c1, lengths=lens)
+        for c in (c1, c2, c1):
+            assert torch.equal(gf(c), m(c))
+            assert torch.equal(gt(c, lengths=lens), m.forward_trimmed(c, lens))
+        m.output_conv[1].bias.add_(0.25)                      # bumps the parameter version -> re-upload + re-capture
+        y = gf(c2)
+        assert torch.equal(y, m(c2))
+        m.output_conv[1].bias.sub_(0.25)
+    with pytest.raises(ValueError):
+        gf(c1[:1])

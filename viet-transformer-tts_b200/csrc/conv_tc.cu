@@ -681,10 +681,13 @@ static int tc_num_sms() {
 
 template <int ROWB, int FMT>
 static int tc_launch_t(const TcLaunch &L, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in shared-memory size is a per-device function attribute: set it once per device, not once per process
+    static bool attr[64] = {};
+    int dev = 0;
+    VTTS_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     VTTS_CHECK_CUDA(launch_kernel_ex(conv_tc_kernel<ROWB, FMT>, L.grid, dim3(TC_THREADS), L.smem, st, L.pdl, (unsigned)L.p.cluster, L.tm_act,
                                      L.tm_w, L.p));
@@ -1137,10 +1140,13 @@ struct TcUnitLaunch {
 
 template <int ROWB, int FMT>
 static int unit_launch_t(const TcUnitLaunch &L, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in shared-memory size is a per-device function attribute: set it once per device, not once per process
+    static bool attr[64] = {};
+    int dev = 0;
+    VTTS_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit_tc_kernel<ROWB, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     VTTS_CHECK_CUDA(launch_kernel_ex(unit_tc_kernel<ROWB, FMT>, L.grid, dim3(TC_THREADS), L.smem, st, L.pdl, 1u, L.tm_act, L.tm_w1, L.tm_w2, L.u));
     return VTTS_OK;
@@ -1679,10 +1685,13 @@ struct TcUnit64Launch {
 
 template <int ROWB, int FMT, int MODE>
 static int unit64_launch_m(const TcUnit64Launch &L, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in shared-memory size is a per-device function attribute: set it once per device, not once per process
+    static bool attr[64] = {};
+    int dev = 0;
+    VTTS_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         VTTS_CHECK_CUDA(cudaFuncSetAttribute(unit64_tc_kernel<ROWB, FMT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     VTTS_CHECK_CUDA(launch_kernel_ex(unit64_tc_kernel<ROWB, FMT, MODE>, L.grid, dim3(V_THREADS), L.smem, st, L.pdl, 1u, L.tm_act, L.tm_w1, L.tm_w2,
                                      L.u));

@@ -8,7 +8,7 @@ reference's ``state_dict`` keys, ctypes calls, batch sharding across ranks.
 from . import _lib
 from .dropin import install, uninstall
 from .gaussian_upsampling import GaussianUpsampling
-from .hifigan import HiFiGAN, ResidualBlock
+from .hifigan import GraphedForward, HiFiGAN, ResidualBlock
 from .length_regulator import LengthRegulator
 from .sharding import gather_waveforms, plan_shards, shard_batch
 from .synthesis import PendingSynthesis, Synthesizer
@@ -16,7 +16,7 @@ from .vits2 import Generator, ResBlock1, ResBlock2
 from .vits2_path import expand_by_path, generate_path
 
 __all__ = [
-    "HiFiGAN", "ResidualBlock", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
+    "HiFiGAN", "ResidualBlock", "GraphedForward", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
     "Synthesizer", "PendingSynthesis", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall", "generate_path",
     "expand_by_path",
 ]

@@ -260,9 +260,72 @@ class _GeneratorBase(nn.Module):
                 return ch, L
         raise ValueError(f"no stage {stage}")
 
+    def graphed(self, c: torch.Tensor, g: Optional[torch.Tensor] = None,
+                lengths: Optional[torch.Tensor] = None) -> "GraphedForward":
+        """Extension for low-latency serving: capture the ~50 launches of one forward at this input shape into a CUDA
+        graph.  ``c`` / ``g`` / ``lengths`` are examples that fix shapes and dtypes; see :class:`GraphedForward`."""
+        return GraphedForward(self, c, g, lengths)
+
     def debug_stage(self, c: torch.Tensor, stage: int, g: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Test hook: intermediate tensor (B, C, L) fp32 of the kernel path (see vtts_gen_forward)."""
         return self._run_kernels(c, g, dump_stage=stage)[1]
+
+
+class GraphedForward:
+    """One generator forward at a fixed (B, T) captured into a CUDA graph (``module.graphed(example_c, ...)``).
+
+    Replaying the graph removes the host cost of the ~50 kernel launches (tensor-map encoding, ctypes calls), which
+    dominates single-utterance latency.  ``__call__`` copies the inputs into the captured buffers, replays and returns
+    the captured output tensor -- valid until the next call.  The capture is redone automatically when a parameter of the
+    module changes (same version signature that triggers the weight re-upload).  Synthesis only.
+    """
+
+    def __init__(self, module: "_GeneratorBase", c: torch.Tensor, g: Optional[torch.Tensor] = None,
+                 lengths: Optional[torch.Tensor] = None):
+        if not c.is_cuda:
+            raise RuntimeError("vtts_b200.GraphedForward: inputs must be CUDA tensors (no CPU fallback)")
+        self._m = module
+        self._c = c.detach().clone()
+        self._g = None if g is None else g.detach().clone()
+        self._len = None if lengths is None else lengths.detach().to(c.device, torch.int64).clone()
+        self._graph = None
+        self._sig = None
+        self._out = None
+
+    def _run(self):
+        if self._len is not None:
+            return self._m.forward_trimmed(self._c, self._len, self._g)
+        return self._m._run_kernels(self._c, self._g)
+
+    def _capture(self):
+        dev = self._c.device
+        with torch.no_grad(), torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._run()                      # warm-up outside capture: weight upload, workspace allocation
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._out = self._run()
+        self._graph, self._sig = graph, self._m._signature()
+
+    @torch.no_grad()
+    def __call__(self, c: torch.Tensor, g: Optional[torch.Tensor] = None,
+                 lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if tuple(c.shape) != tuple(self._c.shape):
+            raise ValueError(f"GraphedForward was captured for {tuple(self._c.shape)}, got {tuple(c.shape)}")
+        if (g is None) != (self._g is None) or (lengths is None) != (self._len is None):
+            raise ValueError("GraphedForward: g / lengths must be given exactly as at capture time")
+        self._c.copy_(c, non_blocking=True)
+        if g is not None:
+            self._g.copy_(g.reshape(self._g.shape), non_blocking=True)
+        if lengths is not None:
+            self._len.copy_(lengths, non_blocking=True)
+        if self._graph is None or self._sig != self._m._signature():
+            self._capture()
+        self._graph.replay()
+        return self._out
 
 
 class HiFiGAN(_GeneratorBase):
