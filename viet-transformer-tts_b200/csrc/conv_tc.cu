@@ -783,6 +783,7 @@ struct TcUnitParams {
     float slope_mid;               // LeakyReLU between conv1 and conv2
     int taps2;                     // conv2 taps (dilation 1)
     int xt_chunks;                 // C / chunk channels
+    int ea_warps;                  // epilogue warps that build the operand tile (4 or 8); the other 16 - ea_warps drain B
 };
 
 template <int ROWB, int FMT>
@@ -816,7 +817,9 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int nbox = (TN + span + BOX_ROWS - 1) / BOX_ROWS;
     const int h2 = (u.taps2 - 1) / 2;
     const int ncta = (int)gridDim.x;
-    const int n_epi = EPI_WARPS / 2;                      // warps per epilogue group (operand / output)
+    // epilogue warps: the first ea_warps (4 or 8) build the operand tile, the rest drain the output accumulator.  The
+    // HBM-bound k=3 units give the output side 12 warps (more loads in flight), the MMA-bound ones keep 8 + 8.
+    const int ea_warps = u.ea_warps, eb_warps = EPI_WARPS - u.ea_warps;
 
     // work items: (time tile of UN2 outputs, batch); m_blocks == 1.  With the padding trim only LIVE tiles are numbered
     // (per-batch offsets in s_ioff, binary search per tile), so the round-robin over CTAs stays balanced.
@@ -835,8 +838,8 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
         for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(accA_full, 1); mbar_init(xt_full, (uint32_t)n_epi);
-        mbar_init(accB_full, 1); mbar_init(accB_empty, (uint32_t)n_epi);
+        mbar_init(accA_full, 1); mbar_init(xt_full, (uint32_t)ea_warps);
+        mbar_init(accB_full, 1); mbar_init(accB_empty, (uint32_t)eb_warps);
         fence_barrier_init();
     }
     constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2;
@@ -993,10 +996,10 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ===== epilogue warps: two groups so that the operand epilogue of tile t+1 (accumulator A -> xt tile in
         // shared memory, warps 0-7) overlaps the output epilogue of tile t (accumulator B -> HBM, warps 8-15) =====
         const int ew = warp, quarter = warp & 3;
-        const bool is_ea = ew < EPI_WARPS / 2;
-        constexpr int SHARERS = EPI_WARPS / 2 / 4;                   // warps per lane quarter within a group (2)
+        const bool is_ea = ew < ea_warps;
+        const int SHARERS = (is_ea ? ea_warps : eb_warps) / 4;       // warps per lane quarter within this group
         const int qpc = 4 / p.rep;
-        const int worker = (quarter / qpc) * SHARERS + ((ew % (EPI_WARPS / 2)) / 4);   // slice of the 16-column groups
+        const int worker = (quarter / qpc) * SHARERS + (is_ea ? ew : ew - ea_warps) / 4;   // slice of the 16-column groups
         const int n_workers = p.rep * SHARERS;
         const int ch = (quarter % qpc) * 32 + lane;                  // channel of this thread (m_blocks == 1)
         const bool row_ok = ch < p.n_total;
@@ -1083,7 +1086,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         const int rows4 = min(UN2 / 4, p.L4 - i0n / 4);
                         const long long off = ((long long)bn * p.L4 + i0n / 4) * p.cout * 4;
                         const int n_lines = rows4 * p.cout / 8;                 // 128-byte lines
-                        for (int l = threadIdx.x - (EPI_WARPS / 2) * 32; l < n_lines; l += (EPI_WARPS / 2) * 32) {
+                        for (int l = threadIdx.x - ea_warps * 32; l < n_lines; l += eb_warps * 32) {
                             if (R) prefetch_l2(p.res + off + (long long)l * 32);
                             if (Cc) prefetch_l2(p.out_x + off + (long long)l * 32);
                         }
@@ -1094,9 +1097,9 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
                 auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4; };
                 if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout);
-                if (ew == EPI_WARPS / 2 && lane == 0) VTTS_TRACE(7);
+                if (ew == ea_warps && lane == 0) VTTS_TRACE(7);
                 mbar_wait_relaxed(accB_full, tl & 1u);
-                if (ew == EPI_WARPS / 2 && lane == 0) VTTS_TRACE(8);
+                if (ew == ea_warps && lane == 0) VTTS_TRACE(8);
                 tc_fence_after();
                 for (int col = worker * 16; col < UN2; col += n_workers * 16) {
                     const int ibase = i0 + col;
@@ -1119,7 +1122,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(accB_empty);
-                if (ew == EPI_WARPS / 2 && lane == 0) VTTS_TRACE(9);
+                if (ew == ea_warps && lane == 0) VTTS_TRACE(9);
                 ++tl;
             }
         }
@@ -1192,6 +1195,13 @@ static int unit_prepare(TcUnitLaunch &L, int fmt, const uint16_t *act, int B, in
     else if (p.chunks == 1) { p.act_stages = 2; p.w_stages = 3; }  // 80 + 96 + 32 KB
     else { p.act_stages = 2; p.w_stages = 4; }                     // 80 + 64 + 64 KB
     L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.xt_chunks = p.chunks;
+    {
+        static int forced = -1;
+        if (forced < 0) { const char *e = getenv("VTTS_UNIT_EA_WARPS"); forced = e ? atoi(e) : 0; }
+        // measured (tools/exp_ea.sh): k=3 units and the accumulating last units of a block are bound by the output
+        // epilogue (-9 % with 12 warps on it); the k=7 / k=11 units want 8 warps on the operand tile (critical path)
+        L.u.ea_warps = (forced == 4 || forced == 8) ? forced : ((k1 + k2 <= 6 || p.accumulate) ? 4 : 8);
+    }
     L.smem = (size_t)p.act_stages * ACT_ROWS * rowb + (size_t)p.w_stages * p.tps * TM * rowb + (size_t)p.chunks * TN * rowb +
              (size_t)(2 * p.act_stages + 2 * p.w_stages + 4) * 8 + 16 + (2 * MAX_TRIM_BATCH + 1) * sizeof(int);
     if (L.smem > 227 * 1024) return set_error(VTTS_E_UNSUPPORTED, "tc unit: %zu B shared memory", L.smem);
@@ -1246,6 +1256,7 @@ struct TcUnit64Params {
     int taps2;
     int n_stream;                  // conv1 taps [0, n_stream) go through the ring, everything else is resident
     int n_res;                     // resident taps: conv1 [n_stream, taps) then conv2 [0, taps2)
+    int ea_warps;                  // epilogue warps building the operand tile (4 or 8); the other 16 - ea_warps drain B
 };
 
 struct EpiLoads2 { float4 r[2]; };
@@ -1347,7 +1358,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
     const int nbox = (VN_A + span + V_BOX - 1) / V_BOX;
     const int ncta = (int)gridDim.x;
-    constexpr int N_GRP = EPI_WARPS / 2;          // warps per epilogue group
+    const int ea_warps = u.ea_warps, eb_warps = EPI_WARPS - u.ea_warps;   // operand / output epilogue warps (4 + 12 or 8 + 8)
 
     // work items: (time tile of VN_B outputs, batch).  With the padding trim only LIVE tiles are numbered (per-batch
     // offsets in s_ioff), so the round-robin over CTAs is balanced; every role walks the same list incrementally - no
@@ -1376,9 +1387,9 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(wres_full, 1);
         mbar_init(&accA_full[0], 1); mbar_init(&accA_full[1], 1);
-        mbar_init(&xt_full[0], N_GRP); mbar_init(&xt_full[1], N_GRP);
+        mbar_init(&xt_full[0], (uint32_t)ea_warps); mbar_init(&xt_full[1], (uint32_t)ea_warps);
         mbar_init(&accB_full[0], 1); mbar_init(&accB_full[1], 1);
-        mbar_init(&accB_empty[0], N_GRP); mbar_init(&accB_empty[1], N_GRP);
+        mbar_init(&accB_empty[0], (uint32_t)eb_warps); mbar_init(&accB_empty[1], (uint32_t)eb_warps);
         fence_barrier_init();
     }
     constexpr int WARP_ACT = EPI_WARPS, WARP_W = EPI_WARPS + 1, WARP_MMA = EPI_WARPS + 2, WARP_MMA_B = EPI_WARPS + 3;
@@ -1546,11 +1557,12 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         // ===== epilogue warps.  Quarter q of the TMEM lanes holds accumulator rows 16q .. 16q+15 in its first 16 lanes;
         // row r is channel r % C (C = 32: two copies of every channel -> two warps per channel share the columns).
         const int ew = warp, quarter = warp & 3;
-        const bool is_ea = ew < N_GRP;
+        const bool is_ea = ew < ea_warps;
+        const int sharers = (is_ea ? ea_warps : eb_warps) / 4;        // warps of this group per lane quarter
         const int chb = (quarter * 16) % p.cout;                      // first channel of this warp's 16 rows
         const int copy = (quarter * 16) / p.cout;
-        const int n_workers = (V_M / p.cout) * (N_GRP / 4);           // warps sharing one channel set
-        const int worker = copy * (N_GRP / 4) + (ew % N_GRP) / 4;
+        const int n_workers = (V_M / p.cout) * sharers;               // warps sharing one channel set
+        const int worker = copy * sharers + (is_ea ? ew : ew - ea_warps) / 4;
         const int fr = lane >> 2, fc = (lane & 3) * 2;                // fragment row (channel) / first column (position)
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t tl = 0;
@@ -1624,9 +1636,9 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     rl[g] = EpiLoads2{};
                     if (R && col < VN_B && group_fast(i0 + col)) load2(rl[g], res_ptr(i0 + col));
                 }
-                if (ew == N_GRP && lane == 0) VTTS_TRACE(7);
+                if (ew == ea_warps && lane == 0) VTTS_TRACE(7);
                 mbar_wait_relaxed(&accB_full[tl & 1u], (tl >> 1) & 1u);
-                if (ew == N_GRP && lane == 0) VTTS_TRACE(8);
+                if (ew == ea_warps && lane == 0) VTTS_TRACE(8);
                 tc_fence_after();
                 const uint32_t t_acc = t_lane + ((tl & 1u) ? COL_B1 : COL_B0);
                 uint32_t r[8];
@@ -1665,7 +1677,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&accB_empty[tl & 1u]);
-                if (ew == N_GRP && lane == 0) VTTS_TRACE(9);
+                if (ew == ea_warps && lane == 0) VTTS_TRACE(9);
             }
         }
     }
@@ -1771,6 +1783,14 @@ static int unit64_prepare(TcUnit64Launch &L, int fmt, const uint16_t *act, int B
         return set_error(VTTS_E_UNSUPPORTED, "tc unit64: weights of conv2 do not fit in shared memory");
     p.act_stages = act_stages; p.w_stages = w_stages;
     L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.n_stream = n_stream; L.u.n_res = n_res;
+    {
+        static int forced = -1;
+        if (forced < 0) { const char *e = getenv("VTTS_UNIT64_EA_WARPS"); forced = e ? atoi(e) : 0; }
+        // measured (tools/exp_ea.sh): 12 output-epilogue warps pay off where that side is the bottleneck (64 ch: k=7 and
+        // the accumulating last unit of a block; 32 ch: k=11), 8 + 8 elsewhere
+        const bool wide_out = (C == 64 && (k1 == 7 || p.accumulate)) || (C == 32 && k1 == 11);
+        L.u.ea_warps = (forced == 4 || forced == 8) ? forced : (wide_out ? 4 : 8);
+    }
     {
         const bool R = p.res != nullptr, Cc = p.accumulate != 0, D = p.divide_by > 0.f, X = p.out_x != nullptr, A = p.out_a != nullptr;
         L.mode = (R && !Cc && !D && X && A) ? EPI_RXA : (R && !Cc && !D && X && !A) ? EPI_RX : (R && Cc && !D && X && !A) ? EPI_RCX
