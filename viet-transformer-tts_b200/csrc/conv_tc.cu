@@ -397,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 if (!tile_live(i0, b)) continue;
                 for (int c = 0; c < p.chunks; ++c) {
                     if (c == 0) VTTS_TRACE(4);
-                    mbar_wait(&act_empty[s], ph ^ 1u);
+                    mbar_wait_producer(&act_empty[s], ph ^ 1u);
                     if (c == 0) VTTS_TRACE(5);
                     mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
                     for (int bx = 0; bx < nbox; ++bx)
@@ -426,7 +426,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 for (int c = 0; c < p.chunks; ++c)
                     for (int j = 0; j < p.taps; j += tps) {
                         if ((c | j) == 0) VTTS_TRACE(6);
-                        mbar_wait(&w_empty[s], ph ^ 1u);
+                        mbar_wait_producer(&w_empty[s], ph ^ 1u);
                         if ((c | j) == 0) VTTS_TRACE(7);
                         // a box past the last tap is zero-filled by TMA: the padded tap contributes nothing
                         mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));   // own + peer shares
@@ -880,7 +880,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 tile_i0(item, i0, b);
                 if (!tile_live(i0, b)) continue;
                 for (int c = 0; c < p.chunks; ++c) {
-                    mbar_wait(&act_empty[s], ph ^ 1u);
+                    mbar_wait_producer(&act_empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
                     for (int bx = 0; bx < nbox; ++bx)
                         tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s],
@@ -904,7 +904,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     const int ntaps = phase == 0 ? p.taps : u.taps2;
                     for (int c = 0; c < p.chunks; ++c)
                         for (int j = 0; j < ntaps; j += tps) {
-                            mbar_wait(&w_empty[s], ph ^ 1u);
+                            mbar_wait_producer(&w_empty[s], ph ^ 1u);
                             mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));
                             tma_load_3d(s_w + (size_t)s * stage_bytes, tm, &w_full[s], c * CH, 0, j);
                             if (++s == W_STAGES) { s = 0; ph ^= 1u; }
@@ -1435,7 +1435,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     if (p.res) bulk_prefetch_l2(p.res + off, bytes);
                     if (p.accumulate && p.divide_by > 0.f) bulk_prefetch_l2(p.out_x + off, bytes);
                 }
-                mbar_wait(&act_empty[s], ph ^ 1u);
+                mbar_wait_producer(&act_empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * V_BOX * ROWB));
                 for (int bx = 0; bx < nbox; ++bx)
                     tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * V_BOX * ROWB, &tm_act, &act_full[s], 0,
@@ -1457,7 +1457,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 uint32_t s = 0, ph = 0;
                 for (Walk w = walk_begin(); w.item < n_items; walk_next(w))
                     for (int j = 0; j < u.n_stream; ++j) {
-                        mbar_wait(&w_empty[s], ph ^ 1u);
+                        mbar_wait_producer(&w_empty[s], ph ^ 1u);
                         mbar_arrive_expect_tx(&w_full[s], (uint32_t)TAPB);
                         tma_load_3d(s_wring + (size_t)s * TAPB, &tm_w1, &w_full[s], 0, 0, j);
                         if (++s == W_STAGES) { s = 0; ph ^= 1u; }

@@ -96,6 +96,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Producers run several stages ahead of the tensor pipe, so their waits for a free stage are long and not latency
+// critical: suspend (VTTS_PRODUCER_SPIN=1 restores the hot poll) instead of burning issue slots and power next to the
+// epilogue warps.
+#ifndef VTTS_PRODUCER_SPIN
+__device__ __forceinline__ void mbar_wait_producer(uint64_t *bar, uint32_t parity) { mbar_wait_relaxed(bar, parity); }
+#else
+__device__ __forceinline__ void mbar_wait_producer(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
+#endif
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
