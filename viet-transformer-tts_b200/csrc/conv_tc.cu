@@ -1,23 +1,25 @@
-// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for the HiFi-GAN generator.
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolutions for the HiFi-GAN generator.
 //
 // Every convolution of the generator (generator.py:132-156, layers.py:93-97) is lowered to
-//     D[n, i] = sum_j sum_ci  Wp[j][n][ci] * X[i + off_j][ci]          (bf16 x bf16 -> fp32)
+//     D[n, i] = sum_j sum_ci  Wp[j][n][ci] * X[i + off_j][ci]          (16-bit x 16-bit -> fp32)
 // with n = output row (out channel, or (phase, out channel) for the polyphase transposed conv,
 // SURVEY.md appendix 9.1), i = time position, off_j = tap_off0 + j * tap_step.
 //
-// Data layout in HBM: activations are channels-last (B, L, C): the bf16 operand copy already has
-// the next layer's LeakyReLU applied; the residual stream stays fp32.  Weights are packed
-// [tap][n_pad][ci_pad] bf16 (K-major rows).
+// Data layout in HBM: the 16-bit operand copy (fp16 by default, bf16 optional) is channels-last (B, L, C) and
+// already has the next layer's LeakyReLU applied; the fp32 residual stream is time-packed (B, L/4, C, 4).
+// Weights are packed [tap][n_pad][ci_pad] (K-major rows).
 //
-// One CTA = 128 output rows (UMMA M, TMEM lanes) x TN=256 time positions (UMMA N, TMEM
-// columns).  The weight tile is the A operand, the activation tile the B operand.  The
-// activation tile is loaded ONCE per 64-channel chunk with its halo (TN + (k-1)*d rows) and
-// every tap reads it through a row-shifted shared-memory descriptor, so a k-tap conv moves the
-// activations HBM/L2 -> SMEM once instead of k times.  Warp roles: activation TMA producer,
-// weight TMA producer, MMA issuer (one elected thread), and epilogue warps that read the
-// accumulator with tcgen05.ld (thread = output channel, registers = consecutive time steps, so
-// a warp's global accesses are 32 consecutive channels of one time step = one 128-byte line)
-// and fuse bias + residual + MRF accumulate/mean + LeakyReLU + bf16 re-quantisation.
+// Three persistent, warp-specialised kernels share the building blocks below (TMA producers, tcgen05.mma issuers,
+// tcgen05.ld epilogues, mbarrier pipelines):
+//   conv_tc_kernel     one conv per launch: 128 output rows x 256 positions per tile, double-buffered accumulator;
+//                      the activation tile is loaded once per 64-channel chunk with its halo and every tap reads it
+//                      through a row-shifted shared-memory descriptor (input conv, upsamples, 256-channel stage)
+//   unit_tc_kernel     conv1 -> LeakyReLU -> conv2 -> + x of a ResidualBlock unit in one launch (128 channels): the
+//                      intermediate never leaves the SM (accumulator -> stmatrix -> swizzled operand tile)
+//   unit64_tc_kernel   the same unit for 32 / 64 channels: M = 64 MMAs, weights resident in shared memory, four
+//                      accumulators, two MMA-issuing warps
+// plus conv_post_tp4_kernel (fp32 output conv + tanh) and the weight packers.  DESIGN.md section 4 has the reasoning
+// and the measurements behind each choice.
 #include "generator.cuh"
 #include "tc_common.cuh"
 
