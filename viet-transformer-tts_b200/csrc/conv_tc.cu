@@ -121,6 +121,8 @@ struct TcConvParams {
     int rep;                   // weight rows replicated `rep` times across the 128 lanes (narrow layers: 128 / n_total)
     int L4;                    // ceil(L_out / 4): fp32 streams are stored time-packed [b][t/4][c][4]
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
+    int reverse;               // walk the tiles last-to-first (alternates per launch: the tail the previous kernel just
+                               // wrote is still in L2 when this kernel starts reading there)
     // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
     // are skipped by every role (their outputs are never needed for the valid part of utterance b)
     const long long *lens;
@@ -306,18 +308,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     // the static round-robin over CTAs stays balanced however the utterance lengths fall (a strided walk over
     // (m, tile, batch) with dead tiles skipped left some CTAs with twice the work of others on the short stages).
     struct TileIter {
-        int item, m, g, b, dm, dg, db, mb, gpb, nb;
+        int item, m, g, b, dm, dg, db, mb, gpb, nb, total, rev;
         const int *ioff;
-        __device__ void init(int first, int step, int m_blocks, int groups, const int *offsets = nullptr, int batch = 0) {
-            mb = m_blocks; gpb = groups; ioff = offsets; nb = batch;
+        __device__ void init(int first, int step, int m_blocks, int groups, const int *offsets = nullptr, int batch = 0,
+                             int n_total = 0, int reverse = 0) {
+            mb = m_blocks; gpb = groups; ioff = offsets; nb = batch; total = n_total; rev = reverse;
             item = first;
-            if (ioff) { b = 0; locate(); return; }
+            if (ioff) { b = rev ? nb - 1 : 0; locate(); return; }
             m = first % mb; int r = first / mb; g = r % gpb; b = r / gpb;
             dm = step % mb; r = step / mb; dg = r % gpb; db = r / gpb;
         }
-        __device__ void locate() {
-            while (b < nb && item >= ioff[b + 1]) ++b;
-            const int r = item - ioff[b];
+        __device__ void locate() {                 // compact numbering; rev walks it last-to-first (see TcConvParams::reverse)
+            if (item >= total) return;
+            const int li = rev ? total - 1 - item : item;
+            if (!rev) { while (b < nb && li >= ioff[b + 1]) ++b; } else { while (b > 0 && li < ioff[b]) --b; }
+            const int r = li - ioff[b];
             g = r / mb; m = r - g * mb;
         }
         __device__ void next(int step) {
@@ -392,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             tma_prefetch_desc(&tm_act);
             uint32_t s = 0, ph = 0, tl = 0;                     // stage index and its parity, kept incrementally
             TileIter ti;
-            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch); ti.item < n_items; ti.next(ncl), ++tl) {
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch, n_items, p.reverse); ti.item < n_items; ti.next(ncl), ++tl) {
                 int n0, i0, b;
                 decode(ti, n0, i0, b);
                 (void)n0;
@@ -421,7 +426,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int tps = p.tps;                               // taps per stage (the box depth of tm_w)
             const size_t stage_bytes = (size_t)W_BYTES * tps;
             TileIter ti;
-            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch); ti.item < n_items; ti.next(ncl), ++tl) {
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch, n_items, p.reverse); ti.item < n_items; ti.next(ncl), ++tl) {
                 int n0, i0w, bw;
                 decode(ti, n0, i0w, bw);
                 if (!tile_live(i0w, bw)) continue;
@@ -462,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int tps = p.tps;
             const uint64_t a_stage_step = A_STAGE_STEP * (uint64_t)tps;
             TileIter ti;
-            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch); ti.item < n_items; ti.next(ncl)) {
+            for (ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch, n_items, p.reverse); ti.item < n_items; ti.next(ncl)) {
                 {
                     int n0m, i0m, bm;
                     decode(ti, n0m, i0m, bm);
@@ -570,7 +575,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
         };
         TileIter ti, tnext;
-        ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch);
+        ti.init(cid, ncl, p.m_blocks, p.groups_per_batch, ioff, p.batch, n_items, p.reverse);
         tnext = ti;
         if (cid < n_items) prefetch_tile(ti);
         // with a single m block and no per-batch bias the thread's bias never changes: load it once
@@ -826,7 +831,9 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     // work items: (time tile of UN2 outputs, batch); m_blocks == 1.  With the padding trim only LIVE tiles are numbered
     // (per-batch offsets in s_ioff, binary search per tile), so the round-robin over CTAs stays balanced.
     const bool trimming = p.lens != nullptr;
+    int n_items = 0;                                       // set once the per-batch offsets exist (below)
     auto tile_i0 = [&](int item, int &i0, int &b) {
+        if (p.reverse) item = n_items - 1 - item;          // last-to-first (see TcConvParams::reverse)
         if (!trimming) { b = item / p.t_tiles; i0 = (item - b * p.t_tiles) * UN2; return; }
         int lo = 0, hi = p.batch - 1;                      // last b with s_ioff[b] <= item
         while (lo < hi) {
@@ -869,7 +876,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tps = p.tps;
-    const int n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
+    n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
     // the prologue above overlapped the previous kernel's tail; the weight producer (constant data only) does not wait
     if (warp != EPI_WARPS + 1) { grid_dep_wait(); grid_dep_launch(); }
 
@@ -1366,23 +1373,32 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     // offsets in s_ioff), so the round-robin over CTAs is balanced; every role walks the same list incrementally - no
     // division on the MMA issuers' path.
     const bool trimming = p.lens != nullptr;
-    struct Walk { int item, t, b; };
-    auto walk_fix = [&](Walk &w) {                // locate (t, b) of w.item
-        if (trimming) {
-            while (w.b < p.batch && w.item >= s_ioff[w.b + 1]) ++w.b;
-            w.t = w.item - s_ioff[w.b];
-        } else if (w.t >= p.t_tiles) {
-            if (p.t_tiles >= ncta) { w.t -= p.t_tiles; ++w.b; }
-            else { w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; }
-        }
-    };
+    const bool rev = p.reverse != 0;              // walk the numbered tiles last-to-first
+    int n_items = 0;                              // set once the per-batch offsets exist (below)
+    struct Walk { int item, t, b; };              // item counts this CTA's steps through the list; (t, b) = tile, batch
     auto walk_begin = [&]() {
-        Walk w; w.item = (int)blockIdx.x;
-        if (trimming) { w.b = 0; w.t = 0; } else { w.b = w.item / p.t_tiles; w.t = w.item - w.b * p.t_tiles; }
-        walk_fix(w);
+        Walk w; w.item = (int)blockIdx.x; w.t = 0; w.b = 0;
+        if (w.item >= n_items) return w;
+        const int li = rev ? n_items - 1 - w.item : w.item;
+        if (trimming) {
+            int lo = 0, hi = p.batch - 1;                              // last b with s_ioff[b] <= li
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_ioff[mid] <= li) lo = mid; else hi = mid - 1; }
+            w.b = lo; w.t = li - s_ioff[lo];
+        } else { w.b = li / p.t_tiles; w.t = li - w.b * p.t_tiles; }
         return w;
     };
-    auto walk_next = [&](Walk &w) { w.item += ncta; w.t += ncta; walk_fix(w); };
+    auto walk_next = [&](Walk &w) {
+        w.item += ncta;
+        if (w.item >= n_items) return;
+        const int li = rev ? n_items - 1 - w.item : w.item;
+        if (trimming) {
+            if (!rev) { while (li >= s_ioff[w.b + 1]) ++w.b; } else { while (li < s_ioff[w.b]) --w.b; }
+            w.t = li - s_ioff[w.b];
+        } else if (p.t_tiles >= ncta) {                                // incremental: at most one wrap per step
+            if (!rev) { w.t += ncta; if (w.t >= p.t_tiles) { w.t -= p.t_tiles; ++w.b; } }
+            else { w.t -= ncta; if (w.t < 0) { w.t += p.t_tiles; --w.b; } }
+        } else { w.b = li / p.t_tiles; w.t = li - w.b * p.t_tiles; }
+    };
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
@@ -1418,7 +1434,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
+    n_items = trimming ? s_ioff[p.batch] : p.total_tiles;
     // programmatic dependent launch: the prologue above - and the resident weight loads below, which do not depend on
     // the previous kernel - overlap that kernel's tail; everything else waits for it here
     if (warp != WARP_W) { grid_dep_wait(); grid_dep_launch(); }
@@ -2115,6 +2131,11 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
         p.len_rate = in_rate;
         p.len_extra = transposed ? p.taps : 0;
     }
+    {
+        static int alt = -1;
+        if (alt < 0) { const char *e = getenv("VTTS_TC_ALTERNATE"); alt = (e && e[0] == '0') ? 0 : 1; }
+        p.reverse = alt ? (h->launch_count & 1) : 0;
+    }
     TcLaunch L;
     int rc = tc_prepare(L, fmt, act, B, L_in, l.ci_pad, l.w16[fmt], pad_to(l.n_total, TM), p);
     if (rc) return rc;
@@ -2140,6 +2161,11 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
         p.len_margin = margin >= 0 ? margin : h->trim_margin;
         p.len_rate = rate;
         p.len_extra = 0;
+    }
+    {
+        static int alt = -1;
+        if (alt < 0) { const char *e = getenv("VTTS_TC_ALTERNATE"); alt = (e && e[0] == '0') ? 0 : 1; }
+        p.reverse = alt ? (h->launch_count & 1) : 0;
     }
     const bool narrow = unit64_usable(l1.info.cout, l1.info.ksize, l1.info.dilation, l2.info.ksize);
     TcUnitLaunch L;
