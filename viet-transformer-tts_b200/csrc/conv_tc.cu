@@ -121,6 +121,7 @@ struct TcConvParams {
     int rep;                   // weight rows replicated `rep` times across the 128 lanes (narrow layers: 128 / n_total)
     int L4;                    // ceil(L_out / 4): fp32 streams are stored time-packed [b][t/4][c][4]
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
+    int stream_hint;           // 1: activation / residual reads carry the L2 evict-first policy
     int reverse;               // walk the tiles last-to-first (alternates per launch: the tail the previous kernel just
                                // wrote is still in L2 when this kernel starts reading there)
     // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
@@ -164,10 +165,10 @@ template <int MODE> struct EpiFlags {
 // residual (and running-sum) values of one 16-column group: 4 x 128-bit loads per stream
 struct EpiLoads { float4 r[4]; };
 template <int C_CT>
-__device__ __forceinline__ void epi_load16(EpiLoads &d, const float *base, int C_rt) {
+__device__ __forceinline__ void epi_load16(EpiLoads &d, const float *base, int C_rt, uint64_t policy) {
     const int C = C_CT ? C_CT : C_rt;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) d.r[m] = __ldg(reinterpret_cast<const float4 *>(base + (size_t)m * C * 4));
+    for (int m = 0; m < 4; ++m) d.r[m] = ldg_f4_hint(base + (size_t)m * C * 4, policy);
 }
 
 // One fully valid 16-column group of a unit-stride layer.  C_CT > 0: compile-time channel count.
@@ -290,6 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     int *s_ioff = s_lim + MAX_TRIM_BATCH;                  // [MAX_TRIM_BATCH + 1] first live work item of every batch row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t pol = l2_policy(p.stream_hint != 0);   // eviction policy of the activation / residual reads
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
@@ -408,8 +410,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     if (c == 0) VTTS_TRACE(5);
                     mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
                     for (int bx = 0; bx < nbox; ++bx)
-                        tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act,
-                                    &act_full[s], c * CH, i0 + min_off + bx * BOX_ROWS, b);
+                        tma_load_3d_hint(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act,
+                                         &act_full[s], c * CH, i0 + min_off + bx * BOX_ROWS, b, pol);
                     if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -610,7 +612,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + co) * 4; };
             // issue the first group's residual loads before waiting for the accumulator
             EpiLoads cur{}, nxt{};
-            if (quarter_used && R && group_fast(i0 + col_lo)) epi_load16<0>(nxt, res_ptr(i0 + col_lo), p.cout);
+            if (quarter_used && R && group_fast(i0 + col_lo)) epi_load16<0>(nxt, res_ptr(i0 + col_lo), p.cout, pol);
             if (ew == 0 && lane == 0) VTTS_TRACE(8);
             mbar_wait_relaxed(&acc_full[buf], (tl / ACC_STAGES) & 1u);
             if (ew == 0 && lane == 0) VTTS_TRACE(9);
@@ -624,7 +626,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TN + (uint32_t)col, v);
                     cur = nxt;
                     const bool fast = group_fast(ibase);
-                    if (R && cg + 16 < cols_per_warp && group_fast(ibase + 16)) epi_load16<0>(nxt, res_ptr(ibase + 16), p.cout);
+                    if (R && cg + 16 < cols_per_warp && group_fast(ibase + 16)) epi_load16<0>(nxt, res_ptr(ibase + 16), p.cout, pol);
                     tmem_ld_wait();
                     if (fast) {
                         float *px = X ? p.out_x + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + co) * 4 : nullptr;
@@ -818,6 +820,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     int *s_ioff = s_lim + MAX_TRIM_BATCH;          // [MAX_TRIM_BATCH + 1] first live tile index of every batch row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t pol = l2_policy(p.stream_hint != 0);   // eviction policy of the activation / residual reads
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
@@ -892,8 +895,8 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     mbar_wait_producer(&act_empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * BOX_ROWS * ROWB));
                     for (int bx = 0; bx < nbox; ++bx)
-                        tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s],
-                                    c * CH, i0 - UXT_OFF + min_off + bx * BOX_ROWS, b);
+                        tma_load_3d_hint(s_act + (size_t)s * ACT_BYTES + (size_t)bx * BOX_ROWS * ROWB, &tm_act, &act_full[s],
+                                         c * CH, i0 - UXT_OFF + min_off + bx * BOX_ROWS, b, pol);
                     if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -1105,7 +1108,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 EpiLoads cur{}, nxt{};
                 auto group_fast = [&](int ibase) { return mode != EPI_GENERIC && rows_full && ibase + 16 <= n_valid; };
                 auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4; };
-                if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout);
+                if (R && worker * 16 < UN2 && group_fast(i0 + worker * 16)) epi_load16<0>(nxt, res_ptr(i0 + worker * 16), p.cout, pol);
                 if (ew == ea_warps && lane == 0) VTTS_TRACE(7);
                 mbar_wait_relaxed(accB_full, tl & 1u);
                 if (ew == ea_warps && lane == 0) VTTS_TRACE(8);
@@ -1118,7 +1121,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     cur = nxt;
                     const bool fast = group_fast(ibase);
                     const int col_n = col + n_workers * 16;
-                    if (R && col_n < UN2 && group_fast(i0 + col_n)) epi_load16<0>(nxt, res_ptr(i0 + col_n), p.cout);
+                    if (R && col_n < UN2 && group_fast(i0 + col_n)) epi_load16<0>(nxt, res_ptr(i0 + col_n), p.cout, pol);
                     tmem_ld_wait();
                     if (fast) {
                         float *px = X ? p.out_x + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + ch) * 4 : nullptr;
@@ -1362,6 +1365,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     int *s_ioff = s_lim + MAX_TRIM_BATCH;          // [MAX_TRIM_BATCH + 1] first live tile index of every batch row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t pol = l2_policy(p.stream_hint != 0);   // eviction policy of the activation / residual reads
     const int last_off = p.tap_off0 + (p.taps - 1) * p.tap_step;
     const int min_off = p.tap_off0 < last_off ? p.tap_off0 : last_off;
     const int span = (p.tap_off0 < last_off ? last_off : p.tap_off0) - min_off;
@@ -1456,8 +1460,8 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 mbar_wait_producer(&act_empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&act_full[s], (uint32_t)(nbox * V_BOX * ROWB));
                 for (int bx = 0; bx < nbox; ++bx)
-                    tma_load_3d(s_act + (size_t)s * ACT_BYTES + (size_t)bx * V_BOX * ROWB, &tm_act, &act_full[s], 0,
-                                i0 - V_XT_OFF + min_off + bx * V_BOX, b);
+                    tma_load_3d_hint(s_act + (size_t)s * ACT_BYTES + (size_t)bx * V_BOX * ROWB, &tm_act, &act_full[s], 0,
+                                     i0 - V_XT_OFF + min_off + bx * V_BOX, b, pol);
                 if (++s == ACT_STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -1642,8 +1646,8 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 auto group_fast = [&](int ibase) { return MODE != EPI_GENERIC && ibase + 16 <= n_valid; };
                 auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + ((ibase >> 2) + pg)) * p.cout + ch) * 4; };
                 auto load2 = [&](EpiLoads2 &d, const float *ptr) {
-                    d.r[0] = __ldg(reinterpret_cast<const float4 *>(ptr));
-                    d.r[1] = __ldg(reinterpret_cast<const float4 *>(ptr + (size_t)2 * p.cout * 4));
+                    d.r[0] = ldg_f4_hint(ptr, pol);
+                    d.r[1] = ldg_f4_hint(ptr + (size_t)2 * p.cout * 4, pol);
                 };
                 // all residual loads of this warp's groups go out before waiting for the accumulator
                 EpiLoads2 rl[V_MAXG];
@@ -2135,6 +2139,9 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
         static int alt = -1;
         if (alt < 0) { const char *e = getenv("VTTS_TC_ALTERNATE"); alt = (e && e[0] == '0') ? 0 : 1; }
         p.reverse = alt ? (h->launch_count & 1) : 0;
+        static int hint = -1;
+        if (hint < 0) { const char *e = getenv("VTTS_TC_STREAM_HINT"); hint = (e && e[0] == '0') ? 0 : 1; }
+        p.stream_hint = hint;
     }
     TcLaunch L;
     int rc = tc_prepare(L, fmt, act, B, L_in, l.ci_pad, l.w16[fmt], pad_to(l.n_total, TM), p);
@@ -2166,6 +2173,9 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
         static int alt = -1;
         if (alt < 0) { const char *e = getenv("VTTS_TC_ALTERNATE"); alt = (e && e[0] == '0') ? 0 : 1; }
         p.reverse = alt ? (h->launch_count & 1) : 0;
+        static int hint = -1;
+        if (hint < 0) { const char *e = getenv("VTTS_TC_STREAM_HINT"); hint = (e && e[0] == '0') ? 0 : 1; }
+        p.stream_hint = hint;
     }
     const bool narrow = unit64_usable(l1.info.cout, l1.info.ksize, l1.info.dilation, l2.info.ksize);
     TcUnitLaunch L;

@@ -122,6 +122,30 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uin
         : "memory");
 }
 
+// L2 eviction policy for streams that are dead after this read (activations, residual): evict-first keeps the lines
+// this kernel WRITES in L2 instead, where the next kernel (which walks the tiles in the opposite direction) finds them.
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+    uint64_t pol;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float *p, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(policy));
+    return v;
+}
+
 // multicast: the box lands at the same shared-memory offset of every CTA in `mask`, and each
 // destination CTA's mbarrier (same offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_3d_mc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
