@@ -435,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 for (int c = 0; c < p.chunks; ++c)
                     for (int j = 0; j < p.taps; j += tps) {
                         if ((c | j) == 0) VTTS_TRACE(6);
-                        mbar_wait_producer(&w_empty[s], ph ^ 1u);
+                        mbar_wait(&w_empty[s], ph ^ 1u);   // hot poll: the weight ring is short and on the critical path
                         if ((c | j) == 0) VTTS_TRACE(7);
                         // a box past the last tap is zero-filled by TMA: the padded tap contributes nothing
                         mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));   // own + peer shares
@@ -916,7 +916,7 @@ unit_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     const int ntaps = phase == 0 ? p.taps : u.taps2;
                     for (int c = 0; c < p.chunks; ++c)
                         for (int j = 0; j < ntaps; j += tps) {
-                            mbar_wait_producer(&w_empty[s], ph ^ 1u);
+                            mbar_wait(&w_empty[s], ph ^ 1u);   // hot poll: the weight ring is short and on the critical path
                             mbar_arrive_expect_tx(&w_full[s], (uint32_t)(p.w_rows * ROWB * tps));
                             tma_load_3d(s_w + (size_t)s * stage_bytes, tm, &w_full[s], c * CH, 0, j);
                             if (++s == W_STAGES) { s = 0; ph ^= 1u; }
@@ -1479,7 +1479,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 uint32_t s = 0, ph = 0;
                 for (Walk w = walk_begin(); w.item < n_items; walk_next(w))
                     for (int j = 0; j < u.n_stream; ++j) {
-                        mbar_wait_producer(&w_empty[s], ph ^ 1u);
+                        mbar_wait(&w_empty[s], ph ^ 1u);   // hot poll: the weight ring is short and on the critical path
                         mbar_arrive_expect_tx(&w_full[s], (uint32_t)TAPB);
                         tma_load_3d(s_wring + (size_t)s * TAPB, &tm_w1, &w_full[s], 0, 0, j);
                         if (++s == W_STAGES) { s = 0; ph ^= 1u; }
