@@ -21,4 +21,16 @@ with torch.no_grad():
     for _ in range(3):
         gf(c)
     b = lat(lambda: gf(c))
+    ts = []
+    for _ in range(30):                      # host time of one launch-path call (no synchronisation inside)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); m(c); ts.append(1e3 * (time.perf_counter() - t0))
+    ts.sort()
+    print("host time of m(c) without sync: median ms", round(ts[len(ts) // 2], 3))
+    import cProfile, pstats, io
+    pr = cProfile.Profile(); pr.enable()
+    for _ in range(20):
+        m(c)
+    pr.disable(); torch.cuda.synchronize()
+    st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(14); print(st.getvalue()[:2500])
 print("env", {k: v for k, v in os.environ.items() if k.startswith("VTTS_")}, "launch median/min", a, "graph median/min", b)

@@ -112,6 +112,7 @@ class _GeneratorBase(nn.Module):
         state = self.__dict__.copy()
         for k in ("_handles", "_uploaded", "_workspace"):
             state[k] = {}
+        state.pop("_layer_cache", None)
         return state
 
     def __del__(self):
@@ -122,8 +123,27 @@ class _GeneratorBase(nn.Module):
         except Exception:
             pass
 
+    _PARAM_NAMES = ("weight_g", "weight_v", "weight", "bias")
+
     def _signature(self) -> tuple:
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Version signature of every tensor the kernels consume (re-upload / re-capture trigger).
+
+        Reads the parameters straight from the layer modules' ``_parameters`` dicts (weight-norm removal and
+        parameter replacement change the entries; in-place updates bump ``_version``; ``.to()`` changes ``data_ptr``)
+        instead of walking ``self.parameters()``: 10x cheaper, and this runs on every forward.
+        """
+        mods = self.__dict__.get("_layer_cache")
+        if mods is None:                      # the layer modules are fixed after construction; indexing ModuleLists is slow
+            mods = self._layer_modules()
+            self.__dict__["_layer_cache"] = mods
+        sig = []
+        for m in mods:
+            ps = m._parameters
+            for n in self._PARAM_NAMES:
+                t = ps.get(n)
+                if t is not None:
+                    sig.append((n, t.data_ptr(), t._version))
+        return tuple(sig)
 
     def _handle(self, dev: torch.device) -> int:
         lib = _lib.load()
