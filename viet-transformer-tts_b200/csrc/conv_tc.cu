@@ -1515,29 +1515,39 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     const uint32_t tmem_d = tmem_base + ((tl & 1u) ? COL_A1 : 0u);
                     uint64_t bdesc = act_desc + (uint64_t)sa * ACT16 + (uint64_t)tap0;
                     uint32_t acc = 0;
-                    int j = 0;
-                    for (; j < n_stream; ++j) {                       // streamed taps (ring)
-                        mbar_wait(&w_full[sw], wph);
+                    // Streamed taps [0, n_stream) come through the weight ring, then the resident ones.  (Interleaving the
+                    // two kinds to spread the ring's refills measured slower.)
+                    // The issuer is latency critical (64-cycle MMAs): descriptors advance by adds only.
+                    uint64_t a_res = w1res_desc + (uint64_t)n_stream * TAP16;            // resident tap n_stream
+                    uint64_t b_res = bdesc + (uint64_t)n_stream * tap_step, b_str = bdesc;
+                    int js = 0, jr = n_stream;
+                    bool ready = n_stream > 0 && mbar_try_wait(&w_full[sw], wph);
+                    while (js < n_stream) {
+                        if (!ready) mbar_wait(&w_full[sw], wph);
                         tc_fence_after();
-                        const uint64_t adesc = wring_desc + (uint64_t)sw * TAP16;
+                        uint32_t sn = sw + 1, pn = wph;
+                        if (sn == W_STAGES) { sn = 0; pn ^= 1u; }
+                        const bool ready_next = mbar_try_wait(&w_full[sn], pn);   // probe early, read after the issue
+                        const uint64_t a_str = wring_desc + (uint64_t)sw * TAP16;
 #pragma unroll
                         for (int ks = 0; ks < KSTEPS; ++ks) {
-                            umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idescA, acc);
+                            umma_bf16(tmem_d, a_str + (uint64_t)(ks * 2), b_str + (uint64_t)(ks * 2), idescA, acc);
                             acc = 1;
                         }
                         umma_commit(&w_empty[sw]);
-                        if (++sw == W_STAGES) { sw = 0; wph ^= 1u; }
-                        bdesc += tap_step;
+                        sw = sn; wph = pn;
+                        ready = ready_next;
+                        ++js;
+                        b_str += tap_step;
                     }
-                    uint64_t adesc = w1res_desc + (uint64_t)j * TAP16;
-                    for (; j < taps1; ++j) {                          // resident taps
+                    for (; jr < taps1; ++jr) {                        // remaining (or all) resident taps
 #pragma unroll
                         for (int ks = 0; ks < KSTEPS; ++ks) {
-                            umma_bf16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idescA, acc);
+                            umma_bf16(tmem_d, a_res + (uint64_t)(ks * 2), b_res + (uint64_t)(ks * 2), idescA, acc);
                             acc = 1;
                         }
-                        adesc += TAP16;
-                        bdesc += tap_step;
+                        a_res += TAP16;
+                        b_res += tap_step;
                     }
                     VTTS_TRACE(11);
                     umma_commit(&act_empty[sa]);
