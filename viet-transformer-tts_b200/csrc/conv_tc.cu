@@ -1269,6 +1269,7 @@ struct TcUnit64Params {
     int n_stream;                  // conv1 taps [0, n_stream) go through the ring, everything else is resident
     int n_res;                     // resident taps: conv1 [n_stream, taps) then conv2 [0, taps2)
     int ea_warps;                  // epilogue warps building the operand tile (4 or 8); the other 16 - ea_warps drain B
+    int xt_bufs;                   // xt tiles in shared memory: 2 (one per tile parity) or 1 (when the weights need the room)
 };
 
 struct EpiLoads2 { float4 r[2]; };
@@ -1351,7 +1352,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     uint8_t *s_wres = s_act + (size_t)ACT_STAGES * ACT_BYTES;
     uint8_t *s_wring = s_wres + (size_t)u.n_res * TAPB;
     uint8_t *s_xt = s_wring + (size_t)W_STAGES * TAPB;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + 2 * XT_BYTES);     // two xt buffers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_xt + (size_t)u.xt_bufs * XT_BYTES);     // one or two xt buffers
     uint64_t *act_full = bars, *act_empty = act_full + ACT_STAGES;
     uint64_t *w_full = act_empty + ACT_STAGES, *w_empty = w_full + W_STAGES;
     uint64_t *wres_full = w_empty + W_STAGES;
@@ -1363,6 +1364,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accB_empty + 2);
     int *s_lim = reinterpret_cast<int *>(tmem_slot + 2);
     int *s_ioff = s_lim + MAX_TRIM_BATCH;          // [MAX_TRIM_BATCH + 1] first live tile index of every batch row
+    volatile int *s_a_issued = s_ioff + MAX_TRIM_BATCH + 1;   // tiles whose conv1 MMAs have been issued (issue-order hand-off)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t pol = l2_policy(p.stream_hint != 0);   // eviction policy of the activation / residual reads
@@ -1408,6 +1410,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         for (uint32_t s = 0; s < ACT_STAGES; ++s) { mbar_init(&act_full[s], 1); mbar_init(&act_empty[s], 1); }
         for (uint32_t s = 0; s < W_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(wres_full, 1);
+        *s_a_issued = 0;
         mbar_init(&accA_full[0], 1); mbar_init(&accA_full[1], 1);
         mbar_init(&xt_full[0], (uint32_t)ea_warps); mbar_init(&xt_full[1], (uint32_t)ea_warps);
         mbar_init(&accB_full[0], 1); mbar_init(&accB_full[1], 1);
@@ -1553,6 +1556,7 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     umma_commit(&act_empty[sa]);
                     if (++sa == ACT_STAGES) { sa = 0; aph ^= 1u; }
                     umma_commit(&accA_full[tl & 1u]);
+                    *s_a_issued = (int)tl + 1;
                     VTTS_TRACE(1);
                 }
             } else {
@@ -1566,10 +1570,22 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     mbar_wait(&xt_full[tl & 1u], (tl >> 1) & 1u);     // operand epilogue wrote xt[tl & 1]
                     VTTS_TRACE(2);
                     mbar_wait(&accB_empty[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // output epilogue of tile tl-2 drained B[tl & 1]
+                    if (ACT_STAGES == 1) {
+                        // Single activation stage (weights fill the rest of shared memory): the stage reloads only after
+                        // conv1 of tile tl+1 has EXECUTED, so that conv1 goes into the MMA queue before this conv2 instead
+                        // of interleaved with it - otherwise both finish together and the pipe idles for the reload.
+                        Walk wn = w;
+                        walk_next(wn);
+                        if (wn.item < n_items) {
+                            const long long t0 = clock64();
+                            while (*s_a_issued < (int)tl + 2)
+                                if (clock64() - t0 > 4000000000LL) mbar_timeout();
+                        }
+                    }
                     VTTS_TRACE(3);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + ((tl & 1u) ? COL_B1 : COL_B0);
-                    uint64_t adesc = w2_desc, bdesc = xt_desc + ((tl & 1u) ? XT16 : 0);
+                    uint64_t adesc = w2_desc, bdesc = xt_desc + (((tl & 1u) && u.xt_bufs == 2) ? XT16 : 0);
                     uint32_t acc = 0;
                     for (int j = 0; j < taps2; ++j) {
 #pragma unroll
@@ -1609,10 +1625,14 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 const int i0 = w.t * VN_B;
                 mbar_wait_relaxed(&accA_full[tl & 1u], (tl >> 1) & 1u);
                 if (ew == 0 && lane == 0) VTTS_TRACE(5);
-                mbar_wait_relaxed(&accB_full[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // conv2 of tile tl-2 finished reading xt[tl & 1]
+                if (u.xt_bufs == 2) {
+                    mbar_wait_relaxed(&accB_full[tl & 1u], ((tl >> 1) & 1u) ^ 1u);   // conv2 of tile tl-2 finished reading xt[tl & 1]
+                } else if (tl > 0) {                              // single xt tile: conv2 of the PREVIOUS tile must be done with it
+                    mbar_wait_relaxed(&accB_full[(tl - 1u) & 1u], ((tl - 1u) >> 1) & 1u);
+                }
                 tc_fence_after();
                 const uint32_t t_acc = t_lane + ((tl & 1u) ? COL_A1 : 0u);
-                const uint32_t xt0 = xt_base + ((tl & 1u) ? (uint32_t)XT_BYTES : 0u);
+                const uint32_t xt0 = xt_base + (((tl & 1u) && u.xt_bufs == 2) ? (uint32_t)XT_BYTES : 0u);
                 const int pos0 = i0 - V_XT_OFF;
                 const bool interior = pos0 >= 0 && pos0 + VN_A <= p.n_pos;
                 uint32_t r[8];
@@ -1764,19 +1784,30 @@ static bool tc_unit64_enabled() {
 }
 
 // shared-memory plan of the narrow unit: returns false when conv2 cannot be fully resident
-static bool unit64_plan(int C, int k1, int k2, int &act_stages, int &w_stages, int &n_stream, int &n_res, size_t &smem) {
+static bool unit64_plan(int C, int k1, int k2, int &act_stages, int &w_stages, int &n_stream, int &n_res, int &xt_bufs,
+                        size_t &smem) {
     const int rowb = C * 2;
-    const size_t tapb = (size_t)V_M * rowb, actb = (size_t)V_ACT_ROWS * rowb, xtb = (size_t)2 * VN_A * rowb;
-    const size_t fixed = xtb + 512 + (2 * MAX_TRIM_BATCH + 1) * sizeof(int);
+    const size_t tapb = (size_t)V_M * rowb, actb = (size_t)V_ACT_ROWS * rowb, xtb = (size_t)VN_A * rowb;
+    const size_t fixed = 512 + (2 * MAX_TRIM_BATCH + 2) * sizeof(int);
     const size_t avail = 227 * 1024;
     const int total = k1 + k2;
+    w_stages = 0; n_stream = 0; n_res = total;
+    // 1. everything resident, one xt tile per parity, 4..2 activation stages
+    xt_bufs = 2;
     for (act_stages = 4; act_stages >= 2; --act_stages) {
-        w_stages = 0; n_stream = 0; n_res = total;
-        smem = fixed + act_stages * actb + (size_t)total * tapb;
+        smem = fixed + 2 * xtb + act_stages * actb + (size_t)total * tapb;
         if (smem <= avail) return true;
     }
-    act_stages = 2; w_stages = 4;
-    const size_t base = fixed + act_stages * actb + w_stages * tapb;
+    // 2. everything resident with a single xt tile and 2..1 activation stages (64 channels x k=11: 176 KB of weights).
+    //    The two MMA issuers keep the pipe busy while the single stage reloads, and no weight ring has to keep up.
+    xt_bufs = 1;
+    for (act_stages = 2; act_stages >= 1; --act_stages) {
+        smem = fixed + xtb + act_stages * actb + (size_t)total * tapb;
+        if (smem <= avail) return true;
+    }
+    // 3. conv2 resident, the conv1 taps that do not fit streamed through a ring
+    xt_bufs = 2; act_stages = 2; w_stages = 4;
+    const size_t base = fixed + 2 * xtb + act_stages * actb + w_stages * tapb;
     if (base + (size_t)k2 * tapb > avail) return false;
     n_res = (int)((avail - base) / tapb);
     if (n_res > total) n_res = total;
@@ -1789,9 +1820,9 @@ static bool unit64_plan(int C, int k1, int k2, int &act_stages, int &w_stages, i
 static bool unit64_usable(int C, int k1, int d1, int k2) {
     if (!tc_unit64_enabled() || (C != 32 && C != 64)) return false;
     if ((k1 - 1) * d1 > HALO_MAX || (k2 - 1) / 2 > V_XT_OFF || k2 < 1) return false;
-    int a, w, ns, nr;
+    int a, w, ns, nr, xb;
     size_t smem;
-    return unit64_plan(C, k1, k2, a, w, ns, nr, smem);
+    return unit64_plan(C, k1, k2, a, w, ns, nr, xb, smem);
 }
 
 static int unit64_prepare(TcUnit64Launch &L, int fmt, const uint16_t *act, int B, int Lpos, int C, const uint16_t *w1, int k1,
@@ -1810,11 +1841,12 @@ static int unit64_prepare(TcUnit64Launch &L, int fmt, const uint16_t *act, int B
     p.L4 = (Lpos + 3) / 4;
     p.batch = B;
     if (p.lens && B > MAX_TRIM_BATCH) p.lens = nullptr;
-    int act_stages, w_stages, n_stream, n_res;
-    if (!unit64_plan(C, k1, k2, act_stages, w_stages, n_stream, n_res, L.smem))
+    int act_stages, w_stages, n_stream, n_res, xt_bufs;
+    if (!unit64_plan(C, k1, k2, act_stages, w_stages, n_stream, n_res, xt_bufs, L.smem))
         return set_error(VTTS_E_UNSUPPORTED, "tc unit64: weights of conv2 do not fit in shared memory");
     p.act_stages = act_stages; p.w_stages = w_stages;
     L.u.e = p; L.u.bias1 = bias1; L.u.slope_mid = slope_mid; L.u.taps2 = k2; L.u.n_stream = n_stream; L.u.n_res = n_res;
+    L.u.xt_bufs = xt_bufs;
     {
         static int forced = -1;
         if (forced < 0) { const char *e = getenv("VTTS_UNIT64_EA_WARPS"); forced = e ? atoi(e) : 0; }
