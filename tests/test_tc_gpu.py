@@ -352,3 +352,19 @@ def test_graphed_forward_replays_bit_identically_and_tracks_weight_updates():
         m.output_conv[1].bias.sub_(0.25)
     with pytest.raises(ValueError):
         gf(c1[:1])
+
+
+def test_padding_trim_with_more_rows_than_the_limit_table():
+    """More batch rows than the kernels' shared-memory length table (256): every row is still computed correctly
+    (the kernels fall back to computing all tiles; the waveform padding is still zero-filled by the output conv)."""
+    m, _ = v1_model("fp16")
+    g = torch.Generator().manual_seed(77)
+    B, T = 260, 6
+    c = torch.randn(B, 80, T, generator=g).to(DEV)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    with torch.no_grad():
+        full = m(c)
+        trimmed = m.forward_trimmed(c, lens.to(DEV))
+    for b in (0, 1, 128, 255, 256, 259):
+        n = int(lens[b]) * 256
+        assert torch.equal(full[b, :, :n], trimmed[b, :, :n])
