@@ -1671,22 +1671,45 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const int pg = (lane & 3) >> 1;                           // which group of 4 positions inside 8 columns
             const float bias2 = p.bias ? __ldg(p.bias + ch) : 0.f;
             const int n_valid = p.n_pos < p.L_out ? p.n_pos : p.L_out;
-            for (Walk w = walk_begin(); w.item < n_items; walk_next(w), ++tl) {
-                const int i0 = w.t * VN_B, b = w.b;
-                auto group_fast = [&](int ibase) { return MODE != EPI_GENERIC && ibase + 16 <= n_valid; };
-                auto res_ptr = [&](int ibase) { return p.res + (((long long)b * p.L4 + ((ibase >> 2) + pg)) * p.cout + ch) * 4; };
-                auto load2 = [&](EpiLoads2 &d, const float *ptr) {
-                    d.r[0] = ldg_f4_hint(ptr, pol);
-                    d.r[1] = ldg_f4_hint(ptr + (size_t)2 * p.cout * 4, pol);
-                };
-                // all residual loads of this warp's groups go out before waiting for the accumulator
-                EpiLoads2 rl[V_MAXG];
-                const int col0 = worker * 16, cstep = n_workers * 16;
+            auto group_fast = [&](int ibase) { return MODE != EPI_GENERIC && ibase + 16 <= n_valid; };
+            auto load2 = [&](EpiLoads2 &d, const float *ptr) {
+                d.r[0] = ldg_f4_hint(ptr, pol);
+                d.r[1] = ldg_f4_hint(ptr + (size_t)2 * p.cout * 4, pol);
+            };
+            const int col0 = worker * 16, cstep = n_workers * 16;
+            // residual of the 16-column group at `col` of the tile at (i0, b): 4 positions + the 4 positions 8 further
+            auto res_ptr = [&](int i0, int b, int col) {
+                return p.res + (((long long)b * p.L4 + (((i0 + col) >> 2) + pg)) * p.cout + ch) * 4;
+            };
+            // 32 channels (at most two groups per warp): the residual of a tile is loaded ONE TILE AHEAD - slot g is refilled
+            // for the next tile right after group g has consumed it, so the L2/HBM latency of these loads never sits
+            // between the accumulator becoming ready and the stores (this epilogue is the pace-maker of the HBM-bound
+            // units).  64 channels (up to four groups per warp): that many loads in flight next to the stores measured
+            // slower, so there the tile's loads go out just before the accumulator wait.  Compile-time split, so neither
+            // variant pays for the other.
+            constexpr bool EARLY = ROWB == 64;
+            EpiLoads2 rl[V_MAXG];
+            Walk w = walk_begin();
 #pragma unroll
-                for (int g = 0; g < V_MAXG; ++g) {
-                    const int col = col0 + g * cstep;
-                    rl[g] = EpiLoads2{};
-                    if (R && col < VN_B && group_fast(i0 + col)) load2(rl[g], res_ptr(i0 + col));
+            for (int g = 0; g < V_MAXG; ++g) {
+                const int col = col0 + g * cstep;
+                rl[g] = EpiLoads2{};
+                if (EARLY && R && w.item < n_items && col < VN_B && group_fast(w.t * VN_B + col))
+                    load2(rl[g], res_ptr(w.t * VN_B, w.b, col));
+            }
+            for (; w.item < n_items; ++tl) {
+                const int i0 = w.t * VN_B, b = w.b;
+                Walk wn = w;
+                walk_next(wn);
+                const bool has_next = wn.item < n_items;
+                const int i0n = wn.t * VN_B, bn = wn.b;
+                if (!EARLY) {
+#pragma unroll
+                    for (int g = 0; g < V_MAXG; ++g) {
+                        const int col = col0 + g * cstep;
+                        rl[g] = EpiLoads2{};
+                        if (R && col < VN_B && group_fast(i0 + col)) load2(rl[g], res_ptr(i0, b, col));
+                    }
                 }
                 if (ew == ea_warps && lane == 0) VTTS_TRACE(7);
                 mbar_wait_relaxed(&accB_full[tl & 1u], (tl >> 1) & 1u);
@@ -1715,16 +1738,19 @@ unit64_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         q[4] = __uint_as_float(r[4]); q[5] = __uint_as_float(r[5]); q[6] = __uint_as_float(x1); q[7] = __uint_as_float(y1);
                     }
                     if (col + cstep < VN_B) tmem_ld_16x256_x2(t_acc + (uint32_t)(col + cstep), r);   // next group's accumulators
-                    if (ibase >= p.n_pos) continue;
-                    const int pos = ibase + pg * 4;                   // first of this thread's 4 positions
-                    if (group_fast(ibase)) {
-                        float *px = X ? p.out_x + (((long long)b * p.L4 + (pos >> 2)) * p.cout + ch) * 4 : nullptr;
-                        uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + pos) * p.out_a_ld + ch : nullptr;
-                        epi64_pair<FMT, CH, MODE == EPI_GENERIC ? EPI_RX : MODE>(q, bias2, p, rl[g], px, pa);
-                    } else {
-                        epi64_pair_edge<FMT>(q, bias2, p, b, pos, ch);
+                    if (ibase < p.n_pos) {
+                        const int pos = ibase + pg * 4;               // first of this thread's 4 positions
+                        if (group_fast(ibase)) {
+                            float *px = X ? p.out_x + (((long long)b * p.L4 + (pos >> 2)) * p.cout + ch) * 4 : nullptr;
+                            uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + pos) * p.out_a_ld + ch : nullptr;
+                            epi64_pair<FMT, CH, MODE == EPI_GENERIC ? EPI_RX : MODE>(q, bias2, p, rl[g], px, pa);
+                        } else {
+                            epi64_pair_edge<FMT>(q, bias2, p, b, pos, ch);
+                        }
                     }
+                    if (EARLY && R && has_next && group_fast(i0n + col)) load2(rl[g], res_ptr(i0n, bn, col));   // next tile
                 }
+                w = wn;
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
