@@ -163,12 +163,13 @@ int vtts_gen_forward(VttsGen *h, const float *c, const float *g, float *wav, int
                      float *dump_out, vtts_stream_t stream);
 
 /* Extension (not in the reference): padding trim for batched synthesis.  mel_len (device, B x int64, or
- * NULL to disable) gives each row's valid mel frames; until reset, the 16-bit path of vtts_gen_forward
- * skips every tile that starts at or beyond (mel_len[b] + margin_frames) frames.  Samples of row b below
- * mel_len[b] * upsample_factor are bit-identical to the untrimmed call provided margin_frames covers the
- * generator's receptive field (14 frames for V1; 16 is the documented default); samples beyond
- * (mel_len[b] + margin_frames) * upsample_factor are zero or undefined.  The pointer must stay valid
- * until the forward has run. */
+ * NULL to disable) gives each row's valid mel frames; until reset, every layer of the 16-bit path of
+ * vtts_gen_forward skips the tiles that cannot reach the first mel_len[b] * upsample_factor samples of row b:
+ * it computes mel_len[b] frames plus the look-ahead its successors need, derived from the handle's kernel
+ * sizes, dilations and scales.  margin_frames adds extra frames on top (a lower bound per layer, never a cap;
+ * pass 0 or a negative value for the derived margins alone).  The valid samples are bit-identical to the
+ * untrimmed call; samples beyond mel_len[b] * upsample_factor are zero or undefined.  The pointer must stay
+ * valid until the forward has run. */
 int vtts_gen_set_valid_lengths(VttsGen *h, const int64_t *mel_len, int margin_frames);
 
 /* Number of kernel launches the last vtts_gen_forward on this handle issued. */
@@ -201,6 +202,14 @@ int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *bias, const 
 int vtts_dbg_trace(int enable, long long *host_out, int n);
 /* Debug: raw tcgen05.mma issue/completion cycles (host_out[0] = issue loop, [1] = until complete). */
 int vtts_dbg_umma_bench(int N, int rowb, int row_shift, int reps, int M, int two_acc, long long *host_out);
+
+/* One ResidualBlock (layers.py:83-98; n_units x [conv1(dil[u]) -> conv2(1)] with identity skips, or conv1 only when
+ * has2 == 0) through the fused chain kernel, channels-first fp32 in / out.  w / bias: HOST arrays of n_units * (1 + has2)
+ * device pointers in reference order (convs1[0], convs2[0], convs1[1], ...), weights (C, C, k).  reps > 0 additionally
+ * times `reps` launches with CUDA events (*ms_out = average milliseconds per launch). */
+int vtts_dbg_resblock_chain(const float *x, const void *const *w, const void *const *bias, float *y, int B, int C,
+                            int L, int k, const int *dil, int n_units, int has2, float slope, int fp16, int reps,
+                            float *ms_out, vtts_stream_t stream);
 
 #ifdef __cplusplus
 }

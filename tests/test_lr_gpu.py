@@ -110,3 +110,33 @@ def test_baseline_shapes_properties(B, Tmax, D):
     for b in range(0, B, max(1, B // 4)):
         n = int(lens[b])
         assert torch.equal(again[b, :n].cpu(), xs[b, :n])
+
+
+def test_expansion_is_differentiable_wrt_xs_like_the_reference():
+    """layers.py:460-462 (repeat_interleave + pad_list) carries gradient from the decoder back to the encoder;
+    the drop-in must too when it is installed under train.py (use_gaussian: false)."""
+    import vtts_b200
+
+    g = torch.Generator().manual_seed(11)
+    B, Tmax, D = 3, 9, 16
+    ds = torch.randint(0, 4, (B, Tmax), generator=g)
+    ds[1, 5:] = 0
+    xs = torch.randn(B, Tmax, D, generator=g)
+    w = None
+    grads = []
+    for impl in ("ref", "new"):
+        x = xs.clone().to("cuda:0").requires_grad_(True)
+        d = ds.clone().to("cuda:0")
+        if impl == "ref":
+            rows = [torch.repeat_interleave(xi, di, dim=0) for xi, di in zip(x, d)]
+            T = max(r.shape[0] for r in rows)
+            out = torch.stack([torch.nn.functional.pad(r, (0, 0, 0, T - r.shape[0])) for r in rows])
+        else:
+            out = vtts_b200.LengthRegulator()(x, d)
+            assert out.requires_grad
+        if w is None:
+            w = torch.randn(out.shape, generator=g).to("cuda:0")
+        (out * w).sum().backward()
+        grads.append((out.detach().cpu(), x.grad.cpu()))
+    assert torch.equal(grads[0][0], grads[1][0])
+    assert torch.allclose(grads[0][1], grads[1][1], atol=1e-6)

@@ -21,6 +21,7 @@
 // plus conv_post_tp4_kernel (fp32 output conv + tanh) and the weight packers.  DESIGN.md section 4 has the reasoning
 // and the measurements behind each choice.
 #include "generator.cuh"
+#include "chain_tc.cuh"
 #include "tc_common.cuh"
 
 #include <map>
@@ -122,6 +123,7 @@ struct TcConvParams {
     int L4;                    // ceil(L_out / 4): fp32 streams are stored time-packed [b][t/4][c][4]
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
     int stream_hint;           // 1: activation / residual reads carry the L2 evict-first policy
+    int x_cl;                  // out_x is channels-last fp32 [b][t][c] (input of the chain kernel) instead of time-packed
     int reverse;               // walk the tiles last-to-first (alternates per launch: the tail the previous kernel just
                                // wrote is still in L2 when this kernel starts reading there)
     // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
@@ -213,7 +215,7 @@ __device__ __forceinline__ void epi_group16_edge(const uint32_t (&v)[16], float 
     for (int e = 0; e < 16; ++e) {
         const long long t = (long long)(ibase + e) * p.out_stride + p.out_off0 + phase;
         if (row_ok && (ibase + e) < p.n_pos && t >= 0 && t < p.L_out) {
-            const long long xo = tp4_off(b, p.L4, t, p.cout, co);
+            const long long xo = p.x_cl ? ((long long)b * p.L_out + t) * p.cout + co : tp4_off(b, p.L4, t, p.cout, co);
             float val = __uint_as_float(v[e]) + bias;
             if (p.res) val = val + __ldg(p.res + xo);
             if (p.accumulate) val = p.out_x[xo] + val;
@@ -235,8 +237,9 @@ __device__ __forceinline__ void epi_group16_poly(const uint32_t (&v)[16], float 
     for (int e = 0; e < 16; ++e) {
         const int t = t_first + e * p.out_stride;
         const float val = __uint_as_float(v[e]) + bias;
-        px_b[(t >> 2) * C4 + (t & 3)] = val;
-        pa_b[t * p.out_a_ld] = cvt16(lrelu_max(val, p.slope_out), FMT);
+        if (p.x_cl) px_b[t * p.cout] = val;       // channels-last: the warp's 32 channels are 128 contiguous bytes
+        else px_b[(t >> 2) * C4 + (t & 3)] = val;
+        if (p.out_a) pa_b[t * p.out_a_ld] = cvt16(lrelu_max(val, p.slope_out), FMT);
     }
 }
 
@@ -550,11 +553,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                        : (R && C && !D && X && !A) ? EPI_RCX
                        : (R && C && D && X && A) ? EPI_RCDXA
                        : (R && C && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
-        const bool unit = p.out_stride == 1 && p.out_off0 == 0 && p.n_total == p.cout && mode != EPI_GENERIC;
+        const bool unit = p.out_stride == 1 && p.out_off0 == 0 && p.n_total == p.cout && mode != EPI_GENERIC && !p.x_cl;
         const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
         // polyphase upsample: fp32 x + 16-bit copy, nothing read; 32-bit index math is safe below 2^31 elements per row
-        const bool poly = !R && !C && !D && X && A && p.out_stride > 1 && (long long)p.L4 * p.cout * 4 < 0x7fffffffLL &&
-                          (long long)p.L_out * p.out_a_ld < 0x7fffffffLL;
+        const bool poly = !R && !C && !D && X && (A || p.x_cl) && p.out_stride > 1 && (long long)p.L4 * p.cout * 4 < 0x7fffffffLL &&
+                          (long long)p.L_out * (A ? p.out_a_ld : 1) < 0x7fffffffLL;
         // L2 prefetch of the fp32 streams the epilogue will read (residual, running MRF sum), one tile ahead,
         // spread over all epilogue threads
         const int et = threadIdx.x;                                // 0 .. EPI_WARPS*32-1
@@ -635,8 +638,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                     } else if (poly && rows_full && ibase + 16 <= p.n_pos &&
                                (long long)ibase * p.out_stride + p.out_off0 + phase >= 0 &&
                                (long long)(ibase + 15) * p.out_stride + p.out_off0 + phase < p.L_out) {
-                        epi_group16_poly<FMT>(v, bias, p, p.out_x + ((long long)b * p.L4 * p.cout + co) * 4,
-                                              p.out_a + (long long)b * p.L_out * p.out_a_ld + co,
+                        epi_group16_poly<FMT>(v, bias, p,
+                                              p.x_cl ? p.out_x + (long long)b * p.L_out * p.cout + co
+                                                     : p.out_x + ((long long)b * p.L4 * p.cout + co) * 4,
+                                              A ? p.out_a + (long long)b * p.L_out * p.out_a_ld + co : nullptr,
                                               ibase * p.out_stride + p.out_off0 + phase);
                     } else {
                         epi_group16_edge<FMT>(v, bias, p, row_ok, b, ibase, phase, co);
@@ -2066,11 +2071,17 @@ int tc_pack_layer(VttsGen *h, int layer, cudaStream_t st) {
         if (!l.w_aux) VTTS_CHECK_CUDA(cudaMalloc(&l.w_aux, (size_t)cin * cout * k * sizeof(float)));
         pack_post_kernel<<<ceil_div(cin * cout * k, 256), 256, 0, st>>>(l.w_fold, l.w_aux, cout, cin, k);
         VTTS_CHECK_LAUNCH();
+        l.w_aux_host.resize((size_t)cin * cout * k);   // conv_post_cl_kernel takes the weights as kernel parameters
+        VTTS_CHECK_CUDA(cudaMemcpyAsync(l.w_aux_host.data(), l.w_aux, l.w_aux_host.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+        VTTS_CHECK_CUDA(cudaStreamSynchronize(st));
     }
     return VTTS_OK;
 }
 
-void tc_destroy(VttsGen *) {}
+void tc_destroy(VttsGen *h) {
+    for (auto &cw : h->chain) chain_free(cw);
+    h->chain.clear();
+}
 
 
 
@@ -2157,7 +2168,7 @@ int tc_workspace_bytes(const VttsGen *h, int B, int T, size_t *bytes) {
 
 namespace {
 // VTTS_PROFILE=1: per-launch CUDA-event timing of the tcgen05 path, printed to stderr after the forward
-struct ProfRec { cudaEvent_t a, b; int kind, cin, cout, k, d, B, L; };
+struct ProfRec { cudaEvent_t a, b; int kind, cin, cout, k, d, B, L; bool trimmed; };
 static std::vector<ProfRec> g_prof;
 static bool prof_enabled() {
     static int on = -1;
@@ -2171,8 +2182,9 @@ static void prof_report() {
     for (auto &r : g_prof) {
         float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
         const double fl = 2.0 * r.cin * r.cout * r.k * (double)r.B * r.L;   // conv: per output step; convT: per input step
-        fprintf(stderr, "[vtts-prof] kind=%d cin=%4d cout=%4d k=%2d d=%d L=%7d  %8.3f ms  %7.1f TFLOP/s\n", r.kind, r.cin,
-                r.cout, r.k, r.d, r.L, ms, fl / (ms * 1e-3) / 1e12);
+        // (with the padding trim active the launch computes fewer positions than B * L: TFLOP/s is then an upper bound)
+        fprintf(stderr, "[vtts-prof] kind=%d cin=%4d cout=%4d k=%2d d=%d L=%7d  %8.3f ms  %7.1f TFLOP/s%s\n", r.kind, r.cin,
+                r.cout, r.k, r.d, r.L, ms, fl / (ms * 1e-3) / 1e12, r.trimmed ? " (full-length FLOPs / trimmed launch)" : "");
         total += ms; tflop += fl;
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
@@ -2219,7 +2231,7 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
     if (prof_enabled()) {
         cudaEventCreate(&pr.a); cudaEventCreate(&pr.b);
         pr.kind = l.info.kind; pr.cin = l.info.cin; pr.cout = l.info.cout; pr.k = l.info.ksize; pr.d = l.info.dilation;
-        pr.B = B; pr.L = transposed ? L_in : L_out;
+        pr.B = B; pr.L = transposed ? L_in : L_out; pr.trimmed = p.lens != nullptr;
         cudaEventRecord(pr.a, st);
     }
     if ((rc = tc_launch(L, st))) return rc;
@@ -2257,7 +2269,7 @@ static int run_unit(VttsGen *h, int fmt, const Layer &l1, const Layer &l2, const
     if (prof_enabled()) {
         cudaEventCreate(&pr.a); cudaEventCreate(&pr.b);
         pr.kind = 2; pr.cin = l1.info.cin; pr.cout = l1.info.cout; pr.k = l1.info.ksize + l2.info.ksize; pr.d = l1.info.dilation;
-        pr.B = B; pr.L = Lpos;
+        pr.B = B; pr.L = Lpos; pr.trimmed = p.lens != nullptr;
         cudaEventRecord(pr.a, st);
     }
     L.pdl = L64.pdl = pdl_enabled() && !prof_enabled();
@@ -2287,13 +2299,48 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         if (!exact) h->trim_lens = nullptr;
     }
     const long long *trim_lens = (const long long *)h->trim_lens;
+    // Stages whose every ResidualBlock fits the fused chain kernel (chain_tc.cu) run ONE launch per block on a
+    // channels-last fp32 stream: the upsample writes x (B, L, C) fp32 only, the blocks combine into the MRF sum.
+    auto chain_spec_of = [&](int C, int j) {
+        ChainSpec s;
+        s.C = C; s.k = cfg.resblock_kernel_sizes[j]; s.n_units = cfg.num_dilations[j]; s.has2 = cfg.use_additional_convs ? 1 : 0;
+        for (int m = 0; m < 3 && m < cfg.num_dilations[j]; ++m) s.dil[m] = cfg.resblock_dilations[j][m];
+        return s;
+    };
+    bool stage_chain[VTTS_MAX_STAGES];
+    for (int i = 0; i < cfg.num_upsamples; ++i) {
+        stage_chain[i] = true;
+        for (int j = 0; j < cfg.num_blocks; ++j)
+            if (cfg.num_dilations[j] > 3 || !chain_spec_usable(chain_spec_of(plan.C[i], j))) stage_chain[i] = false;
+    }
+    if (h->chain_dirty) {
+        h->chain.resize((size_t)cfg.num_upsamples * cfg.num_blocks);
+        for (int i = 0; i < cfg.num_upsamples; ++i) {
+            if (!stage_chain[i]) continue;
+            for (int j = 0; j < cfg.num_blocks; ++j) {
+                const float *wp[CH_MAX_CONVS], *bp[CH_MAX_CONVS];
+                int n = 0;
+                for (int m = 0; m < cfg.num_dilations[j]; ++m) {
+                    const Layer &c1 = h->layers[h->idx_c1[i][j][m]];
+                    wp[n] = c1.w_fold; bp[n] = c1.has_bias ? c1.bias : nullptr; ++n;
+                    if (cfg.use_additional_convs) {
+                        const Layer &c2 = h->layers[h->idx_c2[i][j][m]];
+                        wp[n] = c2.w_fold; bp[n] = c2.has_bias ? c2.bias : nullptr; ++n;
+                    }
+                }
+                if ((rc = chain_pack_raw(chain_spec_of(plan.C[i], j), wp, bp, h->chain[(size_t)i * cfg.num_blocks + j], st))) return rc;
+            }
+        }
+        h->chain_dirty = false;
+    }
     // Per-layer trim margins (mel frames beyond mel_len that a layer still computes).  Walking the generator backwards
     // from the last valid sample: a layer's output is needed E positions past the valid end, its input therefore
-    // E + (taps reach) past it.  The caller's margin (vtts_gen_set_valid_lengths) is an upper bound for every layer.
+    // E + (taps reach) past it.  The caller's margin (vtts_gen_set_valid_lengths) is a LOWER bound (extra safety frames),
+    // never a cap: a configuration with a longer look-ahead than V1 must not stop early and read stale workspace.
     int mg_pre = h->trim_margin, mg_post = h->trim_margin, mg_up[VTTS_MAX_STAGES], mg_mrf[VTTS_MAX_STAGES];
     for (int i = 0; i < VTTS_MAX_STAGES; ++i) mg_up[i] = mg_mrf[i] = h->trim_margin;
     if (trim_lens) {
-        auto cap = [&](long long frames) { return (int)(frames < h->trim_margin ? frames : h->trim_margin); };
+        auto cap = [&](long long frames) { return (int)(frames > h->trim_margin ? frames : h->trim_margin); };
         auto frames_of = [](long long ext, long long r) { return (ext + r) / r + 1; };   // ceil((ext + 1) / r) + 1 spare frame
         long long R[VTTS_MAX_STAGES + 1];
         R[0] = 1;
@@ -2309,6 +2356,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                     rj += (long long)(c1.info.ksize - 1) / 2 * c1.info.dilation;
                     if (cfg.use_additional_convs) rj += (h->layers[h->idx_c2[i][j][m]].info.ksize - 1) / 2;
                 }
+                if (stage_chain[i]) rj += chain_extra_reach(chain_spec_of(plan.C[i], j));   // zero-weight taps of the packed MMAs
                 reach = rj > reach ? rj : reach;
             }
             const long long E_in = E + reach;                        // every unit of the stage is computed this far
@@ -2357,6 +2405,52 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         const Layer &u = h->layers[h->idx_up[i]];
         const int Lo = plan.L[i], C = plan.C[i];
         VTTS_REQUIRE(Lo > 0, "vtts_gen_forward: stage %d output length %d <= 0", i, Lo);
+        const bool last_stage = (i == cfg.num_upsamples - 1);
+        if (stage_chain[i]) {
+            {   // upsample: channels-last fp32 x_u only (the chain kernel builds its own 16-bit operands)
+                TcConvParams p{};
+                p.out_x = bf.x_u; p.x_cl = 1; p.slope_out = 1.f;
+                if ((rc = run_conv(h, fmt, u, cur_a, B, L, Lo, p, st, rate, mg_up[i]))) return rc;
+                rate *= u.stride;
+                if (dump_stage == 2 * i + 1 && dump_out) {
+                    h->launch_count++;
+                    if ((rc = launch_cl_to_cf_f32(bf.x_u, dump_out, B, C, Lo, st))) return rc;
+                }
+            }
+            const int nb = cfg.num_blocks;
+            for (int j = 0; j < nb; ++j) {
+                ChainRun r;
+                r.x = bf.x_u; r.cs = bf.x_cs;
+                if (nb == 1) { r.wr = 2; }
+                else if (j == 0) { r.wr = 0; }
+                else if (j < nb - 1) { r.wr = 1; }
+                else { r.wr = 2; r.rd_cs = 1; r.scale = 1.f / (float)nb; }
+                if (r.wr == 2) {   // c = cs / num_blocks (generator.py:153): fp32 for the output conv, 16-bit for the next upsample
+                    r.out_x = (last_stage || dump_stage == 2 * i + 2) ? bf.x_cs : nullptr;
+                    r.out_a = last_stage ? nullptr : bf.a_c;
+                }
+                r.slope = cfg.lrelu_slope; r.slope_out = cfg.lrelu_slope; r.B = B; r.L = Lo;
+                if (h->trim_lens) { r.lens = (const long long *)h->trim_lens; r.len_margin = mg_mrf[i]; r.len_rate = rate; }
+                r.pdl = pdl_enabled() && !prof_enabled();
+                ProfRec pr{};
+                if (prof_enabled()) {
+                    cudaEventCreate(&pr.a); cudaEventCreate(&pr.b);
+                    pr.kind = 3; pr.cin = C; pr.cout = C; pr.k = cfg.resblock_kernel_sizes[j] * cfg.num_dilations[j] * (cfg.use_additional_convs ? 2 : 1);
+                    pr.d = 0; pr.B = B; pr.L = Lo; pr.trimmed = r.lens != nullptr;
+                    cudaEventRecord(pr.a, st);
+                }
+                if ((rc = chain_launch(h->chain[(size_t)i * nb + j], fmt, r, st))) return rc;
+                if (prof_enabled()) { cudaEventRecord(pr.b, st); g_prof.push_back(pr); }
+                h->launch_count++;
+            }
+            if (dump_stage == 2 * i + 2 && dump_out) {
+                h->launch_count++;
+                if ((rc = launch_cl_to_cf_f32(bf.x_cs, dump_out, B, C, Lo, st))) return rc;
+            }
+            cur_a = bf.a_c;
+            L = Lo;
+            continue;
+        }
         {   // upsample: fp32 residual stream x_u + bf16 operand a_u = lrelu(x_u)
             TcConvParams p{};
             p.out_x = bf.x_u; p.out_a = bf.a_u; p.out_a_ld = C; p.slope_out = cfg.lrelu_slope;
@@ -2364,7 +2458,6 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
             rate *= u.stride;
             if ((rc = dump_f32(2 * i + 1, bf.x_u, C, Lo))) return rc;
         }
-        const bool last_stage = (i == cfg.num_upsamples - 1);
         for (int j = 0; j < cfg.num_blocks; ++j) {
             const float *yx = bf.x_u;
             const uint16_t *ya = bf.a_u;
@@ -2420,6 +2513,13 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         for (int oc = 0; oc < post.info.cout; ++oc) {
             const float *w_oc = wt + (size_t)oc * k * C;
             const float *bias = post.has_bias ? post.bias : nullptr;
+            if (stage_chain[cfg.num_upsamples - 1]) {   // the last stage left its mean channels-last
+                if (post.w_aux_host.size() != (size_t)post.info.cout * k * C) return set_error(VTTS_E_STATE, "conv_post: host weights missing");
+                if ((rc = launch_conv_post_cl(bf.x_cs, post.w_aux_host.data() + (size_t)oc * k * C, bias, wav, B, C, L, k,
+                                              cfg.final_lrelu_slope, post.info.cout, oc, trim_lens, mg_post, rate, pdl, st))) return rc;
+                h->launch_count++;
+                continue;
+            }
 #define VTTS_POST(CC)                                                                                         \
     do {                                                                                                      \
         if (smem > 48 * 1024)                                                                                 \

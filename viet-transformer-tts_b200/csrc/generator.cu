@@ -152,6 +152,7 @@ extern "C" int vtts_gen_load_layer(VttsGen *h, int layer, const float *weight_v,
     } else {
         l.has_bias = false;
     }
+    h->chain_dirty = true;   // chain-kernel packing (all convs of a ResidualBlock together) is redone by the next forward
     rc = tc_pack_layer(h, layer, st);
     if (rc) return rc;
     l.loaded = true;
@@ -314,7 +315,7 @@ extern "C" int vtts_gen_forward(VttsGen *h, const float *c, const float *g, floa
 
 extern "C" int vtts_gen_set_valid_lengths(VttsGen *h, const int64_t *mel_len, int margin_frames) {
     VTTS_REQUIRE(h, "vtts_gen_set_valid_lengths: null handle");
-    VTTS_REQUIRE(margin_frames >= 0, "vtts_gen_set_valid_lengths: negative margin");
+    if (margin_frames < 0) margin_frames = 0;   // auto: the per-layer margins derived from the receptive fields
     h->trim_lens = mel_len;
     h->trim_margin = margin_frames;
     return VTTS_OK;

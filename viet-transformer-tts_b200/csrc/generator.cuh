@@ -15,11 +15,32 @@ struct Layer {
     float *bias = nullptr;   // fp32 (cout) or null
     uint16_t *w16[2] = {nullptr, nullptr};  // tcgen05 packing [tap][n_pad][ci_pad], [0] bf16 / [1] fp16 (conv_tc.cu)
     float *w_aux = nullptr;  // output conv only: fp32 [oc][k][ci] for the channels-last kernel
+    std::vector<float> w_aux_host;  // the same on the host (passed to conv_post_cl_kernel as kernel parameters)
     int ci_pad = 0;          // bf16 packing: padded input channels
     int n_total = 0;         // bf16 packing: rows per tap (cout, or s*cout for polyphase)
     bool has_bias = false;
     bool loaded = false;
 };
+
+namespace tc {
+constexpr int CH_MAX_CONVS = 6;     // 3 units x (conv1, conv2)
+// Shape of one ResidualBlock (models/gan_tts/hifigan/layers.py:16-98; vits2 ResBlock1/2 sublayers.py:215-354)
+struct ChainSpec {
+    int C = 0;              // channels (32 or 64)
+    int k = 0;              // kernel size of every conv of the block
+    int n_units = 0;        // len(dilations), <= 3
+    int has2 = 1;           // use_additional_convs: unit = conv1(d) -> conv2(1); else unit = conv1(d)
+    int dil[3] = {1, 1, 1};
+};
+// Packed weights of one block for the fused chain kernel (chain_tc.cu), owned by the handle.
+struct ChainWeights {
+    uint16_t *w16[2] = {nullptr, nullptr};   // [blocks_total][C][C], tap-reversed with zero pad blocks; [0] bf16 / [1] fp16
+    float *bias = nullptr;                   // [n_convs][C] effective biases (cumulative over the residual stream)
+    ChainSpec spec;
+    int n_convs = 0, blocks_total = 0;
+    bool valid = false;
+};
+}  // namespace tc
 
 struct StageDims {
     int C;      // channels after the upsample of this stage
@@ -41,6 +62,8 @@ struct VttsGen {
     void *tc_state = nullptr;  // tensor-map cache etc. owned by conv_tc.cu
     const int64_t *trim_lens = nullptr;  // device (B) valid mel frames for the NEXT forward (vtts_gen_set_valid_lengths)
     int trim_margin = 0;
+    std::vector<vtts::tc::ChainWeights> chain;   // [stage * num_blocks + block], packed lazily by tc_forward
+    bool chain_dirty = true;                     // a layer was (re)loaded since the last packing
 };
 
 namespace vtts {

@@ -138,9 +138,11 @@ __device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *m
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
+// (plain ld.global, not .nc: these streams were written by the preceding kernel, whose lifetime can overlap this
+// kernel's under programmatic dependent launch - .nc is only defined for data that is read-only for the whole kernel)
 __device__ __forceinline__ float4 ldg_f4_hint(const float *p, uint64_t policy) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p), "l"(policy));
     return v;
@@ -411,6 +413,27 @@ __device__ __forceinline__ void tmem_ld_16x256_x2(uint32_t taddr, uint32_t (&r)[
                  : "r"(taddr)
                  : "memory");
 }
+// 16 lanes x 256 bits x1: the same fragment for 8 columns (r[0], r[1] = lane T/4; r[2], r[3] = lane T/4 + 8;
+// columns 2*(T%4), 2*(T%4)+1)
+__device__ __forceinline__ void tmem_ld_16x256_x1(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+// registers -> TMEM: 32 lanes x 32 consecutive fp32 columns (thread = TMEM lane)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Four 8x8 16-bit matrices, stored transposed: thread T passes the shared-memory address of row T%8 of matrix T/8
 // (16 bytes per row); register i is the thread's fragment of matrix i (element pair (T/4, 2*(T%4)), (T/4, 2*(T%4)+1)),
 // which lands in rows 2*(T%4), 2*(T%4)+1 at 16-bit column T/4.

@@ -29,8 +29,10 @@ class GaussianUpsampling(nn.Module):
         lib = _lib.load()
         if not hs.is_cuda or not ds.is_cuda:
             raise RuntimeError("vtts_b200.GaussianUpsampling: inputs must be CUDA tensors (no CPU fallback)")
-        if hs.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("vtts_b200.GaussianUpsampling: synthesis only (backward is not implemented)")
+        if torch.is_grad_enabled() and (hs.requires_grad or (ds.is_floating_point() and ds.requires_grad)):
+            # training (train.py with use_gaussian: true differentiates through hs AND the durations): the same policy as
+            # the generator shells - run the reference's formula through PyTorch autograd; the kernel is the synthesis path
+            return self._forward_eager(hs, ds, h_masks, d_masks)
         B, T_text, D = hs.shape
         dev = hs.device
         with torch.cuda.device(dev):
@@ -57,3 +59,21 @@ class GaussianUpsampling(nn.Module):
             _lib.check(lib.vtts_gauss_upsample(hs_k.data_ptr(), ds_k.data_ptr(), _lib.ptr(hm), _lib.ptr(dm), out.data_ptr(),
                                                B, T_text, D, T_feats, float(self.delta), stream))
         return out if hs.dtype == torch.float32 else out.to(hs.dtype)
+
+    def _forward_eager(self, hs, ds, h_masks=None, d_masks=None):
+        """Autograd form of layers.py:476-520 (softmax over token centres, then a matmul)."""
+        B = ds.size(0)
+        if ds.sum() == 0:
+            logging.warning(
+                "predicted durations includes all 0 sequences. fill the first element with 1."
+            )
+            ds[ds.sum(dim=1).eq(0)] = 1
+        T_feats = int(ds.sum()) if h_masks is None else h_masks.size(-1)
+        t = torch.arange(0, T_feats, device=ds.device).unsqueeze(0).repeat(B, 1).float()
+        if h_masks is not None:
+            t = t * h_masks.float()
+        c = ds.cumsum(dim=-1) - ds / 2
+        energy = -1 * self.delta * (t.unsqueeze(-1) - c.unsqueeze(1)) ** 2
+        if d_masks is not None:
+            energy = energy.masked_fill(~(d_masks.unsqueeze(1).repeat(1, T_feats, 1)), -float("inf"))
+        return torch.matmul(torch.softmax(energy, dim=2), hs)

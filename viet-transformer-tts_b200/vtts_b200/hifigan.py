@@ -136,7 +136,7 @@ class _GeneratorBase(nn.Module):
         if mods is None:                      # the layer modules are fixed after construction; indexing ModuleLists is slow
             mods = self._layer_modules()
             self.__dict__["_layer_cache"] = mods
-        sig = []
+        sig = [("epoch", self.__dict__.get("_epoch", 0), 0)]
         for m in mods:
             ps = m._parameters
             for n in self._PARAM_NAMES:
@@ -144,6 +144,22 @@ class _GeneratorBase(nn.Module):
                 if t is not None:
                     sig.append((n, t.data_ptr(), t._version))
         return tuple(sig)
+
+    def invalidate(self) -> None:
+        """Force a re-upload (and CUDA-graph re-capture) on the next forward.
+
+        The automatic trigger (:meth:`_signature`) sees parameter replacement and in-place autograd-visible updates
+        (optimizer steps, ``load_state_dict``).  Writes through ``.data`` (``p.data.copy_(ema)``) do not bump the version
+        counter: call this after them.  ``reset_parameters`` / ``remove_weight_norm`` / ``apply_weight_norm`` /
+        ``load_state_dict`` call it themselves.
+        """
+        self._uploaded.clear()
+        self.__dict__["_epoch"] = self.__dict__.get("_epoch", 0) + 1
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        if "_uploaded" in self.__dict__:
+            self.invalidate()
 
     def _handle(self, dev: torch.device) -> int:
         lib = _lib.load()
@@ -195,22 +211,25 @@ class _GeneratorBase(nn.Module):
             return True
         return any(p.requires_grad for p in self.parameters())
 
-    TRIM_MARGIN_FRAMES = 16  # >= receptive field of the V1 generator in mel frames (about 14)
+    # Look-ahead of the V1 generator in mel frames, rounded up (input conv: 12-13 frames).  Accounting only (bench.py
+    # counts lengths + this many frames as computed); the kernels derive their own per-layer margins from the config.
+    TRIM_MARGIN_FRAMES = 16
 
     def forward_trimmed(self, c: torch.Tensor, lengths: torch.Tensor, g: Optional[torch.Tensor] = None,
                         margin_frames: Optional[int] = None) -> torch.Tensor:
         """Extension: like ``forward`` for a padded batch whose rows have ``lengths`` valid frames.
 
-        Work beyond ``lengths[b] + margin_frames`` frames is skipped; the first
-        ``lengths[b] * upsample_factor`` samples of row b are bit-identical to ``forward(c, g)``, later samples
-        are zero or undefined.  Synthesis only (no autograd).
+        Work that cannot reach the first ``lengths[b] * upsample_factor`` samples of row b is skipped: every layer
+        computes ``lengths[b]`` frames plus the look-ahead its successors need (derived from the module's own kernel
+        sizes, dilations and scales; ``margin_frames`` only adds extra frames on top).  Those samples are bit-identical
+        to ``forward(c, g)``, later samples are zero or undefined.  Synthesis only (no autograd).
         """
         if self.precision == "fp32":
             return self._run_kernels(c, g)
         lens = lengths.detach().to(c.device, torch.int64).contiguous()
         if lens.numel() != c.shape[0]:
             raise ValueError("lengths must have one entry per batch row")
-        m = self.TRIM_MARGIN_FRAMES if margin_frames is None else int(margin_frames)
+        m = -1 if margin_frames is None else int(margin_frames)
         return self._run_kernels(c, g, trim=(lens, m))
 
     def _run_kernels(self, c: torch.Tensor, g: Optional[torch.Tensor], dump_stage: int = -1, trim=None):
@@ -441,6 +460,8 @@ class HiFiGAN(_GeneratorBase):
         for m in self.modules():
             if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)):
                 m.weight.data.normal_(0.0, 0.01)
+        if "_uploaded" in self.__dict__:
+            self.invalidate()           # .data writes do not bump the version counter the upload cache keys on
 
     def remove_weight_norm(self):
         for m in self.modules():
@@ -448,11 +469,17 @@ class HiFiGAN(_GeneratorBase):
                 nn.utils.remove_weight_norm(m)
             except ValueError:
                 pass
+        self.__dict__.pop("_layer_cache", None)
+        if "_uploaded" in self.__dict__:
+            self.invalidate()
 
     def apply_weight_norm(self):
         for m in self.modules():
             if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)):
                 nn.utils.weight_norm(m)
+        self.__dict__.pop("_layer_cache", None)
+        if "_uploaded" in self.__dict__:
+            self.invalidate()
 
     # -- plumbing ----------------------------------------------------------------------------
     def _forward_eager(self, c, g=None):

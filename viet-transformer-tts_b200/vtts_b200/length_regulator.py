@@ -23,6 +23,45 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         )
 
 
+class _ExpandFn(torch.autograd.Function):
+    """Frame expansion with a gradient w.r.t. ``xs`` (training, ``train.py`` with ``use_gaussian: false``).
+
+    The reference's repeat_interleave + pad_list (layers.py:460-462) is differentiable w.r.t. ``xs``: frame t of row b is
+    a copy of token ``j(b, t)``, so ``grad_xs[b, j] = sum of grad_out[b, t] over the frames of token j``.  Forward is the
+    CUDA gather; backward is a scatter-add over the same frame->token map, rebuilt from the durations with torch ops
+    (the training backward is not part of the synthesis hot path).
+    """
+
+    @staticmethod
+    def forward(ctx, xs, ds_k, t_out, pad_value):
+        lib = _lib.load()
+        B, Tmax, D = xs.shape
+        dev = xs.device
+        xs_k = xs.detach()
+        xs_k = xs_k if xs_k.is_contiguous() else xs_k.contiguous()
+        out = torch.empty((B, t_out, D), dtype=xs.dtype, device=dev)
+        if out.numel():
+            pad = torch.full((1,), pad_value, dtype=xs.dtype)  # host element bytes
+            _lib.check(lib.vtts_lr_gather(xs_k.data_ptr(), ds_k.data_ptr(), out.data_ptr(), B, Tmax, D, t_out,
+                                          xs.element_size(), pad.data_ptr(), _lib.current_stream(dev)))
+        ctx.save_for_backward(ds_k)
+        ctx.shape = (B, Tmax, D, t_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (ds_k,) = ctx.saved_tensors
+        B, Tmax, D, t_out = ctx.shape
+        cum = ds_k.cumsum(1)                                               # (B, Tmax) exclusive end frame of every token
+        t = torch.arange(t_out, device=ds_k.device).expand(B, t_out).contiguous()
+        tok = torch.searchsorted(cum, t, right=True)                       # frame -> token (== Tmax on the padding)
+        valid = tok < Tmax
+        g = grad_out * valid.unsqueeze(-1).to(grad_out.dtype)
+        grad_xs = torch.zeros((B, Tmax, D), dtype=grad_out.dtype, device=grad_out.device)
+        grad_xs.scatter_add_(1, tok.clamp(max=Tmax - 1).unsqueeze(-1).expand(B, t_out, D), g)
+        return grad_xs, None, None, None
+
+
 class LengthRegulator(nn.Module):
     """Expand token-level features to frame level by repeating each row ``ds[b, i]`` times."""
 
@@ -85,6 +124,9 @@ class LengthRegulator(nn.Module):
                 t_out = int(t_max)
             else:
                 t_out = int(max_len)
+            if torch.is_grad_enabled() and xs.requires_grad:
+                # training (the reference's expansion is differentiable w.r.t. xs): same kernel forward, scatter-add backward
+                return _ExpandFn.apply(xs, ds_k, t_out, float(self.pad_value)), mel_len
             xs_k = xs if xs.is_contiguous() else xs.contiguous()
             out = torch.empty((B, t_out, D), dtype=xs.dtype, device=dev)
             if out.numel():

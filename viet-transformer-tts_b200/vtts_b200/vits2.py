@@ -139,6 +139,8 @@ class Generator(_GeneratorBase):
             remove_weight_norm(layer)
         for blk in self.resblocks:
             blk.remove_weight_norm()
+        self.__dict__.pop("_layer_cache", None)
+        self.invalidate()
 
     # -- plumbing ----------------------------------------------------------------------------
     def _forward_eager(self, x, g=None):
