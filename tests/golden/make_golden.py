@@ -203,14 +203,104 @@ def path_cases():
     print("path_cases ok")
 
 
+def fastspeech2_capture():
+    """a9: tensors captured INSIDE the reference's FastSpeech2.inference (fastspeech2/model.py:194-257) on the C2 recipe
+    (4-layer / 256-hidden transformer blocks, duration predictor bias = log 7), reduced to 3 utterances so the
+    fixture stays small: the regulator's inputs and output as VarianceAdaptor.forward passes them (layers.py:226-233),
+    the final mel, feats_lengths and the reference HiFiGAN's waveform for that mel (Text2Wav.inference order,
+    text2wav/model.py:139-167)."""
+    import math
+    import yaml
+
+    ref_loader.load_length_regulator()
+    from models.tts.fastspeech2.model import FastSpeech2  # type: ignore
+    HiFiGAN, _ = ref_loader.load_hifigan()
+    out = {}
+    for tag, use_gaussian in (("lr", False), ("gauss", True)):
+        with open(os.path.join(ref_loader.REF_ROOT, "config/model_config.yaml")) as fh:
+            cfg = yaml.safe_load(fh)["fastspeech2"]
+        cfg["use_cvae"] = False
+        cfg["encoder_layers"] = cfg["decoder_layers"] = 4
+        cfg["encoder_hidden"] = cfg["decoder_hidden"] = 256
+        cfg["building_block"]["block_type"] = "transformer"
+        cfg["variance"]["learn_alignment"] = False
+        cfg["variance"]["duration_modelling"]["use_gaussian"] = use_gaussian
+        stats = {"pitch": {"min": -2.0, "max": 8.0}, "energy": {"min": -1.5, "max": 7.0}}
+        torch.manual_seed(1234)
+        m = FastSpeech2(n_symbols=131, n_channels=80, hparams=cfg, stats=stats, n_speakers=6).eval()
+        m.variance_adaptor.duration_predictor.linear.bias.data.fill_(math.log(7.0))
+        g = torch.Generator().manual_seed(0)
+        B, T = 3, 24
+        text = torch.randint(1, 131, (B, T), generator=g)
+        tl = torch.tensor([24, 17, 9])
+        text[torch.arange(T)[None] >= tl[:, None]] = 0
+        sids = torch.randint(0, 6, (B,), generator=g)
+        cap = {}
+
+        def pre(mod, args):
+            cap["args"] = [a.clone() if torch.is_tensor(a) else a for a in args]
+
+        def post(mod, args, res):
+            cap["out"] = res.clone()
+            cap["ds_after"] = args[1].clone()
+
+        reg = m.variance_adaptor.length_regulator
+        h1, h2 = reg.register_forward_pre_hook(pre), reg.register_forward_hook(post)
+        with torch.no_grad():
+            mel, feats_lengths, _ = m.inference(sids, text, tl)
+        h1.remove(); h2.remove()
+        out[f"{tag}.xs"] = cap["args"][0].numpy()
+        out[f"{tag}.ds"] = cap["args"][1].numpy()
+        out[f"{tag}.ds_after"] = cap["ds_after"].numpy()
+        if use_gaussian:
+            out[f"{tag}.h_masks"] = cap["args"][2].numpy()
+            out[f"{tag}.d_masks"] = cap["args"][3].numpy()
+        out[f"{tag}.out"] = cap["out"].numpy()
+        out[f"{tag}.feats_lengths"] = feats_lengths.numpy()
+        out[f"{tag}.mel"] = mel.contiguous().numpy()
+        if not use_gaussian:
+            torch.manual_seed(1234)
+            voc = HiFiGAN().eval()
+            with torch.no_grad():
+                wav = voc(mel)
+            out[f"{tag}.wav"] = wav.numpy()
+        print("fastspeech2_capture", tag, tuple(cap["out"].shape), tuple(mel.shape), feats_lengths.tolist())
+    np.savez_compressed(os.path.join(OUT, "fastspeech2_capture.npz"), **out)
+
+
+def hifigan_v1_long():
+    """One full-size comparison for the tile schedule at large L: the reference HiFiGAN V1 (seed 1234) on (4, 80, 1000)
+    (BASELINE config C4's length).  Only a strided sample of the waveform is stored (every 97th sample + the first and
+    last 2,048 of every row); the input is re-drawn from its seed by the test."""
+    HiFiGAN, _ = ref_loader.load_hifigan()
+    torch.manual_seed(1234)
+    m = HiFiGAN().eval()
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(4, 80, 1000, generator=g)
+    with torch.no_grad():
+        y = m(c)
+    L = y.shape[-1]
+    idx = np.unique(np.concatenate([np.arange(0, 2048), np.arange(0, L, 97), np.arange(L - 2048, L)]))
+    np.savez_compressed(os.path.join(OUT, "hifigan_v1_long.npz"), seed=np.int64(5), shape=np.array(c.shape), idx=idx,
+                        y=y[:, 0, idx].numpy(), y_norm=np.float64(y.double().norm()), c_sum=np.float64(c.double().sum()))
+    print("hifigan_v1_long", tuple(y.shape), idx.size)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs /root/reference"
+    only = sys.argv[1:]
+    if only:
+        for name in only:
+            globals()[name]()
+        sys.exit(0)
     path_cases()
     gaussian_cases()
     lr_cases()
     hifigan_small()
     hifigan_v1()
     vits2_small()
+    fastspeech2_capture()
+    hifigan_v1_long()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -94,7 +94,7 @@ if __name__ == "__main__":
         for case in [(32, 3, 100, 1), (32, 3, 1000, 2), (32, 7, 777, 1), (32, 11, 2000, 2), (32, 11, 361, 3),
                      (32, 3, 457, 1), (32, 7, 5000, 1), (64, 3, 500, 2), (64, 7, 1000, 1), (32, 11, 40000, 1)]:
             worst = max(worst, check(*case))
-        worst = max(worst, check(32, 3, 900, 1, dil=(1, 3), has2=False))
+        worst = max(worst, check(32, 3, 900, 1, dil=(1, 1), has2=False))
         worst = max(worst, check(32, 5, 900, 2, dil=(1, 2, 4)))
         worst = max(worst, check(32, 7, 900, 2, fp16=0))
         print("WORST", worst)

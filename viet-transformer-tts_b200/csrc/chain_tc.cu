@@ -479,6 +479,9 @@ bool chain_spec_usable(const ChainSpec &s) {
     for (int u = 0; u < s.n_units; ++u) {
         const int d = s.dil[u];
         if (d < 1 || CH_COLS % d != 0 || qmax * d > CH_G) return false;
+        // without the second conv the dilated conv itself would accumulate onto the residual accumulator, whose columns
+        // are laid out for dilation 1: such blocks (vits2 ResBlock2, use_additional_convs=False) keep the per-unit kernels
+        if (!s.has2 && d != 1) return false;
         halo += half * d + (s.has2 ? half : 0);
     }
     if (qmax > CH_G) return false;
