@@ -70,7 +70,6 @@ CHAIN_CASES = [
     (32, 3, 457, 1, (1, 3, 5), True),
     (64, 3, 500, 2, (1, 3, 5), True),
     (64, 7, 1000, 1, (1, 3, 5), True),
-    (64, 11, 777, 2, (1, 3, 5), True),
     (32, 5, 900, 2, (1, 2, 4), True),        # vits2-style dilations
     (32, 3, 900, 1, (1, 1), False),          # no second conv (only dilation 1 is supported there)
     (32, 11, 40000, 1, (1, 3, 5), True),     # many tiles per CTA pair
@@ -133,11 +132,11 @@ def test_v1_full_size_against_reference_golden(precision, rel_tol, abs_tol):
     assert abs(float(y.double().norm()) - float(z["y_norm"])) <= 2 * rel_tol * float(z["y_norm"])
 
 
-def test_chain_and_unit_paths_agree_on_v1(monkeypatch):
-    """The chain kernel replaces 9 unit launches per narrow stage; both paths stay available (VTTS_TC_CHAIN=0 is read at
-    first use, so the unit path is exercised through a 48-channel generator here) and must agree with the fp32 kernels."""
+def test_chain_and_unit_kernels_mix_in_one_forward():
+    """A 3-stage generator 128 / 64 / 32: the 32-channel stage runs the chain kernel, the 64-channel one keeps the
+    per-unit kernels when one of its blocks does not fit (k = 11 at 64 channels); both must agree with the fp32 kernels."""
     torch.manual_seed(3)
-    m = vtts_b200.HiFiGAN(channels=256)           # stages 128 / 64 / 32 / 16: 64 and 32 run the chain, 16 the units
+    m = vtts_b200.HiFiGAN(channels=256, upsample_scales=[8, 4, 2], upsample_kernel_sizes=[16, 8, 4])
     m = m.to(DEV).eval()
     c = torch.randn(2, 80, 50, generator=torch.Generator().manual_seed(1)).to(DEV)
     with torch.no_grad():
@@ -147,4 +146,4 @@ def test_chain_and_unit_paths_agree_on_v1(monkeypatch):
         m.precision = "fp32"
         ref = m(c)
     assert rel_l2(y, ref) <= 1e-3 and max_abs(y, ref) <= 1e-2
-    assert n_launch < 52                           # fewer launches than the unit-per-launch schedule
+    assert n_launch <= 2 + 3 + 18 + 9 + 3 + 1      # layout + input conv, upsamples, stage 0 convs, stage 1 units, stage 2 chains, output conv

@@ -31,6 +31,7 @@
 #include "tc_common.cuh"
 
 #include <stdlib.h>
+#include <vector>
 
 namespace vtts {
 namespace tc {
@@ -60,7 +61,11 @@ struct ChainParams {
     int sps, spc, n_slots, resident, blocks_total;
     const long long *lens;
     int len_margin, len_rate;
+    long long *trace;              // debug (VTTS_CHAIN_TRACE=1 in vtts_dbg_resblock_chain): clock64 stamps of block 0
 };
+constexpr int CH_TRACE_PAIRS = 12, CH_TRACE_STRIDE = 32;   // per (pair, slot): conv i -> 4 stamps; 24.. = init / final
+#define CH_TRACE(pair_, s_, e_) do { if (p.trace && blockIdx.x == 0 && (pair_) < CH_TRACE_PAIRS) \
+    p.trace[(((pair_) * 2) + (s_)) * CH_TRACE_STRIDE + (e_)] = clock64(); } while (0)
 
 // max(v, v*slope) == LeakyReLU for 0 <= slope <= 1 (checked on the host)
 __device__ __forceinline__ float lrelu_fast(float v, float slope) { return fmaxf(v, v * slope); }
@@ -92,8 +97,12 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);
     int *s_lim = reinterpret_cast<int *>(s_bias + CH_MAX_CONVS * C);
     int *s_ioff = s_lim + CH_MAX_TRIM_BATCH;
+    // s_tab[conv i][phase][accumulator column]: operand row (plane * CH_NR + row) that column's value goes to when the
+    // operand planes of conv i are built (source: x for i == 0, else the output of conv i-1)
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_ioff + CH_MAX_TRIM_BATCH + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffle broadcast: tells the compiler the warp index is warp-uniform, so role-specific state can live in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     constexpr int WARP_TMA = CH_EPI_WARPS, WARP_MMA = CH_EPI_WARPS + 1;
     const bool trimming = p.lens != nullptr;
     const int nsl = p.k + PH - 1;                   // MMA slices per conv
@@ -109,6 +118,15 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
     // operand planes start as zeros: the guard rows are never written again
     for (int i = threadIdx.x; i < 2 * OPNDB / 16; i += CH_THREADS) reinterpret_cast<uint4 *>(s_op)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < p.n_convs * C; i += CH_THREADS) s_bias[i] = __ldg(p.bias + i);
+    for (int e = threadIdx.x; e < p.n_convs * PH * CH_N; e += CH_THREADS) {
+        const int col = e & (CH_N - 1), php = (e / CH_N) & (PH - 1), i = e / (CH_N * PH);
+        const int d_src = (i == 0 || p.cx[i - 1]) ? 1 : p.cd[i - 1], d_dst = p.cd[i];
+        const int n = col / d_src;
+        const int tau = d_src * (PH * n + php) + (col - n * d_src);
+        const int u = tau / d_dst, rho = tau - u * d_dst;
+        const int row = (u & (PH - 1)) * CH_NR + CH_G + rho + d_dst * (u >> LOGPH);
+        s_tab[e] = (uint16_t)(col < CH_COLS ? row : 0);
+    }
     if (trimming)
         for (int i = threadIdx.x; i < p.B; i += CH_THREADS) {
             const long long lim = (__ldg(p.lens + i) + p.len_margin) * (long long)p.len_rate;
@@ -173,73 +191,78 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
             }
         }
     } else if (warp == WARP_MMA) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_16(128, CH_N, FMT);
-            constexpr uint64_t ROW16 = ROWB >> 4, PLANE16 = PLANEB >> 4, BLK16 = BLKB >> 4;
-            const uint64_t op_desc[2] = {make_smem_desc(smem_u32(s_op), ROWB, 0), make_smem_desc(smem_u32(s_op + OPNDB), ROWB, 0)};
-            const uint64_t w_desc = make_smem_desc(smem_u32(s_w), ROWB, 0);
-            uint32_t nf[2] = {0u, 0u};
-            uint32_t slot = 0, par = 0;
-            if (p.resident) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
-            // first slice: s' = PH - 1 + half, descending
-            const int sp0 = PH - 1 + ch_half;
-            const int r0 = sp0 & (PH - 1), q0 = sp0 >> LOGPH;
-            for (int j = 0; item_li(j) < n_items; j += 2) {
-                const int npair = item_li(j + 1) < n_items ? 2 : 1;
-                for (int i = 0; i < p.n_convs; ++i) {
-                    const uint64_t dstep = (uint64_t)p.cd[i] * ROW16;
-                    const uint32_t slot_c = slot, par_c = par;
-                    for (int s = 0; s < npair; ++s) {
-                        mbar_wait(&opnd_full[s], nf[s] & 1u);
-                        ++nf[s];
-                        tc_fence_after();
-                        const uint32_t tmem_d = tmem_base + (uint32_t)s * 256u + (p.cx[i] ? 0u : 128u);
-                        uint32_t acc = p.cx[i] ? 1u : 0u;
-                        uint64_t b = op_desc[s] + (uint64_t)r0 * PLANE16 + (uint64_t)CH_G * ROW16 + (uint64_t)q0 * dstep;
-                        int r = r0;
-                        slot = slot_c; par = par_c;
-                        for (int st = 0; st < p.spc; ++st) {
-                            uint64_t a;
-                            if (p.resident) {
-                                a = w_desc + (uint64_t)(i * nsl + st * p.sps) * BLK16;
-                            } else {
-                                mbar_wait(&w_full[slot], par);
-                                tc_fence_after();
-                                a = w_desc + (uint64_t)slot * (uint64_t)slot_blocks * BLK16;
-                            }
-                            const int rest = nsl - st * p.sps;
-                            const int ns = rest < p.sps ? rest : p.sps;
-                            for (int ul = 0; ul < ns; ++ul) {
-#pragma unroll
-                                for (int ks = 0; ks < KSTEPS; ++ks) {
-                                    umma_bf16(tmem_d, a + (uint64_t)(ks * 2), b + (uint64_t)(ks * 2), idesc, acc);
-                                    acc = 1u;
-                                }
-                                a += BLK16;
-                                if (r == 0) { r = PH - 1; b += (uint64_t)(PH - 1) * PLANE16; b -= dstep; }
-                                else { --r; b -= PLANE16; }
-                            }
-                            if (!p.resident) {
-                                if (s == npair - 1) umma_commit(&w_empty[slot]);
-                                if (++slot == (uint32_t)p.n_slots) { slot = 0; par ^= 1u; }
-                            }
+        // the whole warp runs this loop converged with warp-uniform operands (descriptors live in uniform registers: a
+        // single-lane loop pays an R2UR round trip per descriptor word and issues one MMA per ~150 cycles); elect.sync
+        // inside the helpers picks the issuing lane
+        constexpr uint32_t idesc = make_idesc_16(128, CH_N, FMT);
+        constexpr uint64_t ROW16 = ROWB >> 4, PLANE16 = PLANEB >> 4, BLK16 = BLKB >> 4;
+        const uint64_t op_desc[2] = {make_smem_desc(smem_u32(s_op), ROWB, 0), make_smem_desc(smem_u32(s_op + OPNDB), ROWB, 0)};
+        const uint64_t w_desc = make_smem_desc(smem_u32(s_w), ROWB, 0);
+        uint32_t nf[2] = {0u, 0u};
+        uint32_t slot = 0, par = 0;
+        if (p.resident) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
+        // first slice: s' = PH - 1 + half, descending
+        const int sp0 = PH - 1 + ch_half;
+        const int r0 = sp0 & (PH - 1), q0 = sp0 >> LOGPH;
+        for (int j = 0; item_li(j) < n_items; j += 2) {
+            const int npair = item_li(j + 1) < n_items ? 2 : 1;
+            for (int i = 0; i < p.n_convs; ++i) {
+                const uint64_t dstep = (uint64_t)p.cd[i] * ROW16;
+                const uint32_t slot_c = slot, par_c = par;
+                for (int s = 0; s < npair; ++s) {
+                    mbar_wait(&opnd_full[s], nf[s] & 1u);
+                    ++nf[s];
+                    tc_fence_after();
+                    if (lane == 0) CH_TRACE(j >> 1, s, i * 4 + 2);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)s * 256u + (p.cx[i] ? 0u : 128u);
+                    uint32_t acc = p.cx[i] ? 1u : 0u;
+                    uint64_t b = op_desc[s] + (uint64_t)r0 * PLANE16 + (uint64_t)CH_G * ROW16 + (uint64_t)q0 * dstep;
+                    int r = r0;
+                    slot = slot_c; par = par_c;
+                    for (int st = 0; st < p.spc; ++st) {
+                        uint64_t a;
+                        if (p.resident) {
+                            a = w_desc + (uint64_t)(i * nsl + st * p.sps) * BLK16;
+                        } else {
+                            mbar_wait(&w_full[slot], par);
+                            tc_fence_after();
+                            a = w_desc + (uint64_t)slot * (uint64_t)slot_blocks * BLK16;
                         }
-                        umma_commit(&acc_full[s]);
+                        const int rest = nsl - st * p.sps;
+                        const int ns = rest < p.sps ? rest : p.sps;
+                        for (int ul = 0; ul < ns; ++ul) {
+                            umma_slice_warp<KSTEPS>(tmem_d, a, b, idesc, acc);
+                            acc = 1u;
+                            a += BLK16;
+                            if (r == 0) { r = PH - 1; b += (uint64_t)(PH - 1) * PLANE16; b -= dstep; }
+                            else { --r; b -= PLANE16; }
+                        }
+                        if (!p.resident) {
+                            if (s == npair - 1) umma_commit_elect(&w_empty[slot]);
+                            if (++slot == (uint32_t)p.n_slots) { slot = 0; par ^= 1u; }
+                        }
                     }
+                    umma_commit_elect(&acc_full[s]);
+                    if (lane == 0) CH_TRACE(j >> 1, s, i * 4 + 3);
                 }
             }
         }
+        __syncwarp();
     } else {
         // ===== epilogue warps: quarter q of the TMEM lanes = rows 32q .. 32q+31 = (phase, channel) =====
+        // (instruction-lean on purpose: 16 warps x 6 convs per tile made this kernel issue-bound - interior tiles take
+        // paths without per-element bounds checks, the position -> operand-row map comes from a table)
         const int quarter = warp & 3, part = warp >> 2;
         const int ph = C == 32 ? quarter : (quarter >> 1);
         const int chq = C == 32 ? 0 : (quarter & 1) * 32;          // first channel of this quarter
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int col_lo = part * 32;
-        const int fr = lane >> 2, fc = (lane & 3) * 2;              // fragment row (channel in group) / first column
+        const int ncol = col_lo + 32 <= CH_COLS ? 32 : CH_COLS - col_lo;   // live accumulator columns of this warp
+        const int fc = (lane & 3) * 2;                              // fragment: first column
         const int mrow = lane & 7;                                  // stmatrix: operand row this thread addresses
         const uint32_t mchunk = (uint32_t)(chq / 8 + (lane >> 3));  // 16-byte chunk (8 channels) of matrix lane/8
         const uint32_t op_base[2] = {smem_u32(s_op), smem_u32(s_op + OPNDB)};
+        const int bfr = chq + (lane >> 2);                          // fragment row -> channel (rows fr, fr+8, fr+16, fr+24)
         uint32_t na[2] = {0u, 0u};
         Item cur[2] = {{0, 0}, {0, 0}};
         bool has[2] = {false, false};
@@ -251,96 +274,128 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
             const int n = (int)(((uint32_t)col * magic) >> 16);
             return d * (PH * n + ph) + (col - n * d);
         };
-        // tile-relative position -> byte offset of its operand row in the planes laid out for a conv of dilation d
-        auto dst_of = [&](int tau, int d, uint32_t magic) {
-            const int u = (int)(((uint32_t)tau * magic) >> 16);
-            const int rho = tau - u * d;
-            return (uint32_t)((u & (PH - 1)) * PLANEB + (CH_G + rho + d * (u >> LOGPH)) * ROWB);
-        };
-        // TMEM accumulator -> operand planes of the next conv
-        auto build_operand = [&](int s, uint32_t t_acc, int d_src, uint32_t m_src, const float *bias4, int d_dst,
-                                 uint32_t m_dst, const Item &it) {
+        // TMEM accumulator -> operand planes of conv `nxt` (s_tab[nxt]: accumulator column -> operand row)
+        auto build_operand = [&](int s, uint32_t t_acc, int d_src, uint32_t m_src, const float *bias4, int nxt, const Item &it) {
             const bool edge = it.T0 < 0 || it.T0 + W > p.L;
-            const float b0 = bias4 ? bias4[chq + fr] : 0.f, b1 = bias4 ? bias4[chq + fr + 8] : 0.f;
-            const float b2 = bias4 ? bias4[chq + fr + 16] : 0.f, b3 = bias4 ? bias4[chq + fr + 24] : 0.f;
+            const float b0 = bias4 ? bias4[bfr] : 0.f, b1 = bias4 ? bias4[bfr + 8] : 0.f;
+            const float b2 = bias4 ? bias4[bfr + 16] : 0.f, b3 = bias4 ? bias4[bfr + 24] : 0.f;
+            const uint16_t *tab = s_tab + (nxt * PH + ph) * CH_N + col_lo + mrow;
+            const float slope = p.slope;
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
+                if (g8 * 8 >= ncol) break;
                 const int col = col_lo + g8 * 8;
-                if (col >= CH_COLS) break;
                 uint32_t ra[4], rb[4];
                 tmem_ld_16x256_x1(t_acc + (uint32_t)col, ra);
                 tmem_ld_16x256_x1(t_acc + (16u << 16) + (uint32_t)col, rb);
+                const uint32_t off = (uint32_t)tab[g8 * 8] * (uint32_t)ROWB;
+                const uint32_t swz = ROWB == 128 ? ((off >> 7) & 7u) : ((off >> 7) & 3u);
+                const uint32_t dst = op_base[s] + off + ((mchunk ^ swz) << 4);
                 tmem_ld_wait();
                 float v[8];
-                v[0] = lrelu_fast(__uint_as_float(ra[0]) + b0, p.slope); v[1] = lrelu_fast(__uint_as_float(ra[1]) + b0, p.slope);
-                v[2] = lrelu_fast(__uint_as_float(ra[2]) + b1, p.slope); v[3] = lrelu_fast(__uint_as_float(ra[3]) + b1, p.slope);
-                v[4] = lrelu_fast(__uint_as_float(rb[0]) + b2, p.slope); v[5] = lrelu_fast(__uint_as_float(rb[1]) + b2, p.slope);
-                v[6] = lrelu_fast(__uint_as_float(rb[2]) + b3, p.slope); v[7] = lrelu_fast(__uint_as_float(rb[3]) + b3, p.slope);
+                v[0] = lrelu_fast(__uint_as_float(ra[0]) + b0, slope); v[1] = lrelu_fast(__uint_as_float(ra[1]) + b0, slope);
+                v[2] = lrelu_fast(__uint_as_float(ra[2]) + b1, slope); v[3] = lrelu_fast(__uint_as_float(ra[3]) + b1, slope);
+                v[4] = lrelu_fast(__uint_as_float(rb[0]) + b2, slope); v[5] = lrelu_fast(__uint_as_float(rb[1]) + b2, slope);
+                v[6] = lrelu_fast(__uint_as_float(rb[2]) + b3, slope); v[7] = lrelu_fast(__uint_as_float(rb[3]) + b3, slope);
                 if (edge) {                                         // every conv zero-pads its own input
                     const int t0 = it.T0 + tau_of(col + fc, d_src, m_src), t1 = it.T0 + tau_of(col + fc + 1, d_src, m_src);
                     if (t0 < 0 || t0 >= p.L) v[0] = v[2] = v[4] = v[6] = 0.f;
                     if (t1 < 0 || t1 >= p.L) v[1] = v[3] = v[5] = v[7] = 0.f;
                 }
-                const uint32_t off = dst_of(tau_of(col + mrow, d_src, m_src), d_dst, m_dst);
-                const uint32_t swz = ROWB == 128 ? ((off >> 7) & 7u) : ((off >> 7) & 3u);
-                stmatrix_x4_trans(op_base[s] + off + ((mchunk ^ swz) << 4), cvt16x2(v[0], v[1], FMT), cvt16x2(v[2], v[3], FMT),
-                                  cvt16x2(v[4], v[5], FMT), cvt16x2(v[6], v[7], FMT));
+                stmatrix_x4_trans(dst, cvt16x2(v[0], v[1], FMT), cvt16x2(v[2], v[3], FMT), cvt16x2(v[4], v[5], FMT),
+                                  cvt16x2(v[6], v[7], FMT));
             }
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&opnd_full[s]);
         };
-        // x tile (fp32 channels-last) -> residual accumulator X of slot s; thread = TMEM lane = (phase, channel)
+        // x tile (fp32 channels-last) -> residual accumulator X of slot s; thread = TMEM lane = (phase, channel),
+        // register c = accumulator column col_lo + c = position T0 + PH * (col_lo + c) + ph
         auto init_x = [&](int s, const Item &it) {
-            const int ch = chq + lane;
-            const float *xb = p.x + ((long long)it.b * p.L + it.T0 + ph) * C + ch;
+            const float *xb = p.x + ((long long)it.b * p.L + it.T0 + ph + PH * col_lo) * C + chq + lane;
             uint32_t v[32];
-            const bool interior = it.T0 >= 0 && it.T0 + W <= p.L;
+            if (it.T0 >= 0 && it.T0 + W <= p.L && ncol == 32) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int n = col_lo + c;
-                const int t = it.T0 + PH * n + ph;
-                const bool ok = n < CH_COLS && (interior || (t >= 0 && t < p.L));
-                v[c] = ok ? __float_as_uint(ld_stream_f32(xb + (long long)n * (PH * C))) : 0u;
+                for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(ld_stream_f32(xb + c * (PH * C)));
+            } else {
+                // live columns: c < ncol and 0 <= T0 + PH * (col_lo + c) + ph < L
+                const int base_t = it.T0 + ph + PH * col_lo;
+                int c_lo = base_t >= 0 ? 0 : (-base_t + PH - 1) >> LOGPH;
+                int c_hi = (p.L - base_t + PH - 1) >> LOGPH;
+                c_hi = p.L <= base_t ? 0 : (c_hi < ncol ? c_hi : ncol);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = (c >= c_lo && c < c_hi) ? __float_as_uint(ld_stream_f32(xb + c * (PH * C))) : 0u;
             }
             tmem_st_32x32(t_lane + (uint32_t)s * 256u + (uint32_t)col_lo, v);
             tmem_st_wait();
         };
         // residual accumulator X of slot s -> global (the block's output, combined into the MRF sum)
         auto final_out = [&](int s, const Item &it, const float *bias_last) {
-            const int ch = chq + lane;
-            const float bv = bias_last[ch];
+            // valid columns of this warp: tile-relative position PH * (col_lo + c) + ph in [halo, min(halo + V, L - T0))
+            const int hi_tau = p.halo + p.V < p.L - it.T0 ? p.halo + p.V : p.L - it.T0;
+            const int rel = ph + PH * col_lo;
+            int c_lo = p.halo <= rel ? 0 : (p.halo - rel + PH - 1) >> LOGPH;
+            int c_hi = hi_tau <= rel ? 0 : (hi_tau - rel + PH - 1) >> LOGPH;
+            if (c_hi > ncol) c_hi = ncol;
+            if (c_lo >= c_hi) return;
+            const float bv = bias_last[chq + lane];
             uint32_t v[32];
             tmem_ld_32x32(t_lane + (uint32_t)s * 256u + (uint32_t)col_lo, v);
-            const long long base = ((long long)it.b * p.L + it.T0 + ph) * C + ch;
+            const long long base = ((long long)it.b * p.L + it.T0 + rel) * C + chq + lane;
+            const bool full = c_lo == 0 && c_hi == 32;
+            constexpr int CS = PH * C;                              // floats between two columns of one phase
             float old[32];
             if (p.rd_cs) {
+                const float *cp = p.cs + base;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int tau = PH * (col_lo + c) + ph;
-                    const bool ok = tau >= p.halo && tau < p.halo + p.V && it.T0 + tau < p.L;
-                    old[c] = ok ? ld_stream_f32(p.cs + base + (long long)(col_lo + c) * (PH * C)) : 0.f;
-                }
+                for (int c = 0; c < 32; ++c) old[c] = (full || (c >= c_lo && c < c_hi)) ? ld_stream_f32(cp + c * CS) : 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) old[c] = 0.f;
             }
             tmem_ld_wait();
+            if (p.wr == 0) {
+                float *o = p.cs + base;
+                if (full) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int tau = PH * (col_lo + c) + ph;
-                const bool ok = tau >= p.halo && tau < p.halo + p.V && it.T0 + tau < p.L;
-                if (!ok) continue;
-                const long long o = base + (long long)(col_lo + c) * (PH * C);
-                float val = __uint_as_float(v[c]) + bv;
-                if (p.rd_cs) val = old[c] + val;
-                if (p.wr == 0) {
-                    p.cs[o] = val;
-                } else if (p.wr == 1) {
-                    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.cs + o), "f"(val) : "memory");
+                    for (int c = 0; c < 32; ++c) o[c * CS] = __uint_as_float(v[c]) + bv + old[c];
                 } else {
-                    val *= p.scale;
-                    if (p.out_x) p.out_x[o] = val;
-                    if (p.out_a) p.out_a[o] = cvt16(lrelu_fast(val, p.slope_out), FMT);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if (c >= c_lo && c < c_hi) o[c * CS] = __uint_as_float(v[c]) + bv + old[c];
                 }
+            } else if (p.wr == 1) {
+                float *o = p.cs + base;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (full || (c >= c_lo && c < c_hi))
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + c * CS), "f"(__uint_as_float(v[c]) + bv + old[c]) : "memory");
+            } else {
+                float *ox = p.out_x ? p.out_x + base : nullptr;
+                uint16_t *oa = p.out_a ? p.out_a + base : nullptr;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (full || (c >= c_lo && c < c_hi)) {
+                        const float val = (__uint_as_float(v[c]) + bv + old[c]) * p.scale;
+                        if (ox) ox[c * CS] = val;
+                        if (oa) oa[c * CS] = cvt16(lrelu_fast(val, p.slope_out), FMT);
+                    }
+                }
+            }
+        };
+        // L2 prefetch of the x (and MRF-sum) ranges of this CTA's NEXT pair of tiles: their first touch is init_x, whose
+        // latency nothing hides (both slots reach the end of their chains together)
+        auto prefetch_pair = [&](int j) {
+            int bh = bhint;
+            for (int s = 0; s < 2; ++s) {
+                const int li = item_li(j + s);
+                if (li >= n_items) break;
+                const Item it = locate(li, bh);
+                const int t0 = it.T0 < 0 ? 0 : it.T0, t1 = it.T0 + W < p.L ? it.T0 + W : p.L;
+                if (t1 <= t0) continue;
+                const long long o = ((long long)it.b * p.L + t0) * C;
+                bulk_prefetch_l2(p.x + o, (uint32_t)(t1 - t0) * C * 4u);
+                if (p.rd_cs) bulk_prefetch_l2(p.cs + o, (uint32_t)(t1 - t0) * C * 4u);
             }
         };
 
@@ -353,17 +408,23 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                     mbar_wait_relaxed(&acc_full[s], na[s] & 1u);
                     ++na[s];
                     tc_fence_after();
+                    if (warp == 0 && lane == 0) CH_TRACE((j >> 1) - 1, s, 26);
                     final_out(s, cur[s], s_bias + last * C);
+                    if (warp == 0 && lane == 0) CH_TRACE((j >> 1) - 1, s, 27);
                     has[s] = false;
                 }
                 if (more && item_li(j + s) < n_items) {
                     cur[s] = locate(item_li(j + s), bhint);
                     has[s] = true;
+                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, 24);
                     init_x(s, cur[s]);
-                    build_operand(s, t_lane + (uint32_t)s * 256u, 1, 65536u, nullptr, p.cd[0], p.cmagic[0], cur[s]);
+                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, 25);
+                    build_operand(s, t_lane + (uint32_t)s * 256u, 1, 65536u, nullptr, 0, cur[s]);
+                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, 28);
                 }
             }
             if (!more) break;
+            if (warp == 0 && lane == 0) prefetch_pair(j + 2);
             for (int i = 0; i < last; ++i) {
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -372,8 +433,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                     ++na[s];
                     tc_fence_after();
                     const bool from_x = p.cx[i] != 0;
+                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, i * 4 + 0);
                     build_operand(s, t_lane + (uint32_t)s * 256u + (from_x ? 0u : 128u), from_x ? 1 : p.cd[i],
-                                  from_x ? 65536u : p.cmagic[i], s_bias + i * C, p.cd[i + 1], p.cmagic[i + 1], cur[s]);
+                                  from_x ? 65536u : p.cmagic[i], s_bias + i * C, i + 1, cur[s]);
+                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, i * 4 + 1);
                 }
             }
         }
@@ -436,7 +499,8 @@ static ChainPlan chain_plan(const ChainSpec &s) {
     const int nsl = s.k + PH - 1;
     const size_t blkb = (size_t)s.C * rowb;
     const size_t opnd = 2 * (size_t)PH * CH_NR * rowb;
-    const size_t fixed = (4 + 2 * CH_MAX_SLOTS) * 8 + 16 + (size_t)CH_MAX_CONVS * s.C * 4 + (2 * CH_MAX_TRIM_BATCH + 2) * 4 + 64;
+    const size_t fixed = (4 + 2 * CH_MAX_SLOTS) * 8 + 16 + (size_t)CH_MAX_CONVS * s.C * 4 + (2 * CH_MAX_TRIM_BATCH + 2) * 4 +
+                         (size_t)CH_MAX_CONVS * PH * CH_N * 2 + 64;
     pl.blocks_total = n_convs * nsl + PH - 1;
     if (opnd + fixed > (size_t)CH_SMEM_MAX) return pl;
     const size_t avail = (size_t)CH_SMEM_MAX - opnd - fixed;
@@ -578,6 +642,7 @@ int chain_launch(const ChainWeights &cw, int fmt, const ChainRun &r, cudaStream_
     if (total > 0x3fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "chain: too many tiles");
     p.total_items = (int)total;
     p.sps = pl.sps; p.spc = pl.spc; p.n_slots = pl.n_slots; p.resident = pl.resident; p.blocks_total = pl.blocks_total;
+    p.trace = r.trace;
     if (r.lens && r.B <= CH_MAX_TRIM_BATCH) { p.lens = r.lens; p.len_margin = r.len_margin; p.len_rate = r.len_rate; }
     CUtensorMap tm;
     {
@@ -717,6 +782,30 @@ extern "C" int vtts_dbg_resblock_chain(const float *x, const void *const *w, con
     r.x = xcl; r.cs = ycl; r.out_x = ycl; r.wr = 2; r.scale = 1.f; r.slope = slope; r.slope_out = slope; r.B = B; r.L = L;
     if (!rc) rc = chain_launch(cw, fp16 ? VTTS_FMT_FP16 : VTTS_FMT_BF16, r, st);
     if (!rc) rc = launch_cl_to_cf_f32(ycl, y, B, C, L, st);
+    if (!rc && getenv("VTTS_CHAIN_TRACE")) {   // debug: per-conv pipeline stamps of block 0 (second launch: warm caches)
+        const int n = CH_TRACE_PAIRS * 2 * CH_TRACE_STRIDE;
+        long long *dt = nullptr;
+        std::vector<long long> ht(n);
+        cudaMalloc(&dt, n * sizeof(long long));
+        cudaMemsetAsync(dt, 0, n * sizeof(long long), st);
+        r.trace = dt;
+        rc = chain_launch(cw, fp16 ? VTTS_FMT_FP16 : VTTS_FMT_BF16, r, st);
+        r.trace = nullptr;
+        cudaMemcpyAsync(ht.data(), dt, n * sizeof(long long), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        cudaFree(dt);
+        const long long t0 = ht[24];
+        for (int pr = 0; pr < CH_TRACE_PAIRS; ++pr)
+            for (int sl = 0; sl < 2; ++sl) {
+                const long long *e = ht.data() + (pr * 2 + sl) * CH_TRACE_STRIDE;
+                if (!e[24]) continue;
+                fprintf(stderr, "[chain-trace] pair %2d slot %d: init %lld ld+st %lld build0 %lld |", pr, sl, e[24] - t0, e[25] - e[24], e[28] - e[25]);
+                for (int i = 0; i < n_convs; ++i)
+                    fprintf(stderr, " c%d mma[wait@%lld issue %lld] epi[acc@%lld build %lld]", i, e[i * 4 + 2] - t0, e[i * 4 + 3] - e[i * 4 + 2],
+                            i < n_convs - 1 ? e[i * 4 + 0] - t0 : e[26] - t0, i < n_convs - 1 ? e[i * 4 + 1] - e[i * 4 + 0] : e[27] - e[26]);
+                fprintf(stderr, "\n");
+            }
+    }
     if (!rc && reps > 0 && ms_out) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);

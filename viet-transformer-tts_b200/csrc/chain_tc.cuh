@@ -18,6 +18,7 @@ struct ChainRun {
     const long long *lens = nullptr;   // padding trim (see TcConvParams)
     int len_margin = 0, len_rate = 0;
     bool pdl = false;
+    long long *trace = nullptr;        // debug: device buffer for block 0's pipeline stamps (chain_tc.cu)
 };
 
 bool chain_spec_usable(const ChainSpec &s);

@@ -369,6 +369,39 @@ __device__ __forceinline__ uint32_t umma_step4x2_warp(uint32_t tmem_d, uint64_t 
         : "memory");
     return ready;
 }
+// One K-slice of KSTEPS (2 or 4) 16-element steps, whole converged warp with warp-uniform operands (descriptors stay in
+// uniform registers); elect.sync picks the issuing lane.  No barrier traffic: the caller commits once per accumulator.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_slice_warp(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint32_t idesc, uint32_t acc_first) {
+    static_assert(KSTEPS == 2 || KSTEPS == 4, "KSTEPS");
+    if (KSTEPS == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p, t, e;\n\t.reg .b64 a, b;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.eq.b32 t, 0, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "add.u64 a, %1, 2;\n\tadd.u64 b, %2, 2;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t}"
+            ::"r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, t, e;\n\t.reg .b64 a, b;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.eq.b32 t, 0, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "add.u64 a, %1, 2;\n\tadd.u64 b, %2, 2;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+            "add.u64 a, %1, 4;\n\tadd.u64 b, %2, 4;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+            "add.u64 a, %1, 6;\n\tadd.u64 b, %2, 6;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t}"
+            ::"r"(tmem_d), "l"(a0), "l"(b0), "r"(idesc), "r"(acc_first)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {   // whole converged warp; one lane commits
     asm volatile(
         "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
