@@ -41,7 +41,7 @@ constexpr int CH_N = 128;          // UMMA N (columns 120..127 are scratch)
 constexpr int CH_G = 16;           // zero guard rows in front of / behind the data rows of an operand plane
 constexpr int CH_NR = 160;         // rows per operand plane: 16 + 128 + 16
 constexpr int CH_EPI_WARPS = 16;   // 4 per TMEM lane quarter, each owns 32 accumulator columns
-constexpr int CH_THREADS = (CH_EPI_WARPS + 2) * 32;
+constexpr int CH_THREADS = (CH_EPI_WARPS + 3) * 32;   // + weight loader + one MMA issuer per tile slot
 constexpr int CH_MAX_SLOTS = 8;    // weight ring slots
 constexpr int CH_MAX_TRIM_BATCH = 256;
 constexpr int CH_SMEM_MAX = 227 * 1024;
@@ -103,7 +103,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
 
     // (shuffle broadcast: tells the compiler the warp index is warp-uniform, so role-specific state can live in uniform registers)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    constexpr int WARP_TMA = CH_EPI_WARPS, WARP_MMA = CH_EPI_WARPS + 1;
+    constexpr int WARP_TMA = CH_EPI_WARPS, WARP_MMA = CH_EPI_WARPS + 1;   // MMA issuers: warps WARP_MMA (slot 0), WARP_MMA + 1 (slot 1)
     const bool trimming = p.lens != nullptr;
     const int nsl = p.k + PH - 1;                   // MMA slices per conv
     const int ch_half = (p.k - 1) / 2;
@@ -111,7 +111,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
     if (threadIdx.x == 0) {
         mbar_init(&opnd_full[0], CH_EPI_WARPS); mbar_init(&opnd_full[1], CH_EPI_WARPS);
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-        for (int s = 0; s < CH_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < CH_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }   // both issuers release a stage
         fence_barrier_init();
     }
     if (warp == WARP_MMA) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -190,44 +190,48 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                         }
             }
         }
-    } else if (warp == WARP_MMA) {
-        // the whole warp runs this loop converged with warp-uniform operands (descriptors live in uniform registers: a
-        // single-lane loop pays an R2UR round trip per descriptor word and issues one MMA per ~150 cycles); elect.sync
-        // inside the helpers picks the issuing lane
+    } else if (warp == WARP_MMA || warp == WARP_MMA + 1) {
+        // ===== MMA issuers: one warp per tile slot.  A single warp issued the MMAs of both tiles back to back and was
+        // issue-bound (~95 cycles per N=128 MMA against 64 on the tensor pipe); two warps on two schedulers overlap their
+        // issue overhead.  Each warp runs its loop converged with warp-uniform operands (a single-lane loop pays an R2UR
+        // round trip per descriptor word); elect.sync inside the helpers picks the issuing lane.  Streamed weight stages are
+        // shared by the two tiles of a pair: both issuers wait for a stage and both release it. =====
+        const int s = warp - WARP_MMA;
         constexpr uint32_t idesc = make_idesc_16(128, CH_N, FMT);
         constexpr uint64_t ROW16 = ROWB >> 4, PLANE16 = PLANEB >> 4, BLK16 = BLKB >> 4;
-        const uint64_t op_desc[2] = {make_smem_desc(smem_u32(s_op), ROWB, 0), make_smem_desc(smem_u32(s_op + OPNDB), ROWB, 0)};
+        const uint64_t op_desc = make_smem_desc(smem_u32(s_op + (size_t)s * OPNDB), ROWB, 0);
         const uint64_t w_desc = make_smem_desc(smem_u32(s_w), ROWB, 0);
-        uint32_t nf[2] = {0u, 0u};
+        uint32_t nf = 0u;
         uint32_t slot = 0, par = 0;
         if (p.resident) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
         // first slice: s' = PH - 1 + half, descending
         const int sp0 = PH - 1 + ch_half;
         const int r0 = sp0 & (PH - 1), q0 = sp0 >> LOGPH;
         for (int j = 0; item_li(j) < n_items; j += 2) {
-            const int npair = item_li(j + 1) < n_items ? 2 : 1;
+            const bool has = s == 0 || item_li(j + 1) < n_items;   // an odd last pair: slot 1 only keeps the ring in step
+            if (!has && p.resident) break;
             for (int i = 0; i < p.n_convs; ++i) {
                 const uint64_t dstep = (uint64_t)p.cd[i] * ROW16;
-                const uint32_t slot_c = slot, par_c = par;
-                for (int s = 0; s < npair; ++s) {
-                    mbar_wait(&opnd_full[s], nf[s] & 1u);
-                    ++nf[s];
+                if (has) {
+                    mbar_wait(&opnd_full[s], nf & 1u);
+                    ++nf;
                     tc_fence_after();
                     if (lane == 0) CH_TRACE(j >> 1, s, i * 4 + 2);
-                    const uint32_t tmem_d = tmem_base + (uint32_t)s * 256u + (p.cx[i] ? 0u : 128u);
-                    uint32_t acc = p.cx[i] ? 1u : 0u;
-                    uint64_t b = op_desc[s] + (uint64_t)r0 * PLANE16 + (uint64_t)CH_G * ROW16 + (uint64_t)q0 * dstep;
-                    int r = r0;
-                    slot = slot_c; par = par_c;
-                    for (int st = 0; st < p.spc; ++st) {
-                        uint64_t a;
-                        if (p.resident) {
-                            a = w_desc + (uint64_t)(i * nsl + st * p.sps) * BLK16;
-                        } else {
-                            mbar_wait(&w_full[slot], par);
-                            tc_fence_after();
-                            a = w_desc + (uint64_t)slot * (uint64_t)slot_blocks * BLK16;
-                        }
+                }
+                const uint32_t tmem_d = tmem_base + (uint32_t)s * 256u + (p.cx[i] ? 0u : 128u);
+                uint32_t acc = p.cx[i] ? 1u : 0u;
+                uint64_t b = op_desc + (uint64_t)r0 * PLANE16 + (uint64_t)CH_G * ROW16 + (uint64_t)q0 * dstep;
+                int r = r0;
+                for (int st = 0; st < p.spc; ++st) {
+                    uint64_t a;
+                    if (p.resident) {
+                        a = w_desc + (uint64_t)(i * nsl + st * p.sps) * BLK16;
+                    } else {
+                        mbar_wait(&w_full[slot], par);
+                        tc_fence_after();
+                        a = w_desc + (uint64_t)slot * (uint64_t)slot_blocks * BLK16;
+                    }
+                    if (has) {
                         const int rest = nsl - st * p.sps;
                         const int ns = rest < p.sps ? rest : p.sps;
                         for (int ul = 0; ul < ns; ++ul) {
@@ -237,11 +241,14 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                             if (r == 0) { r = PH - 1; b += (uint64_t)(PH - 1) * PLANE16; b -= dstep; }
                             else { --r; b -= PLANE16; }
                         }
-                        if (!p.resident) {
-                            if (s == npair - 1) umma_commit_elect(&w_empty[slot]);
-                            if (++slot == (uint32_t)p.n_slots) { slot = 0; par ^= 1u; }
-                        }
                     }
+                    if (!p.resident) {
+                        if (has) umma_commit_elect(&w_empty[slot]);
+                        else if (lane == 0) mbar_arrive(&w_empty[slot]);
+                        if (++slot == (uint32_t)p.n_slots) { slot = 0; par ^= 1u; }
+                    }
+                }
+                if (has) {
                     umma_commit_elect(&acc_full[s]);
                     if (lane == 0) CH_TRACE(j >> 1, s, i * 4 + 3);
                 }
@@ -517,7 +524,9 @@ static ChainPlan chain_plan(const ChainSpec &s) {
         const size_t slotb = (size_t)(sps + PH - 1) * blkb;
         int n_slots = (int)(avail / slotb);
         if (n_slots > CH_MAX_SLOTS) n_slots = CH_MAX_SLOTS;
-        if (n_slots >= spc + 1) {
+        // (the two MMA issuers walk the stages of a conv side by side and release each stage together: a ring of three
+        // stages keeps one load in flight; it need not hold a whole conv)
+        if (n_slots >= 3 || (n_slots >= 2 && sps == 1)) {
             pl.resident = 0; pl.sps = sps; pl.spc = spc; pl.n_slots = n_slots;
             pl.smem = opnd + (size_t)n_slots * slotb + fixed;
             pl.ok = true;
