@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- synthesized audio seconds per second (inverse RTF) of the hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16|bf16|fp32]
+                    [--config c2|c1|c3|c4|c5|lr] [--quick]
 
-Workload (BASELINE.json configs[1]): FastSpeech2 (4-layer, 256-hidden) LengthRegulator +
-HiFi-GAN V1, batch 16 synthetic phoneme sequences per GPU: hidden states (16, 120, 256) fp32,
-integer durations 1..11 inside each utterance's text length (40..120), 0 outside ->
-LengthRegulator -> (acoustic decoder stand-in: first 80 features as the mel) -> HiFi-GAN V1
--> 22.05 kHz waveform.  Random-init weights drawn with torch.manual_seed(1234).
+Headline workload (BASELINE.json configs[1], `--config c2`, the default): FastSpeech2 (4-layer, 256-hidden)
+LengthRegulator + HiFi-GAN V1, batch 16 synthetic phoneme sequences per GPU: hidden states (16, 120, 256) fp32,
+integer durations 1..11 inside each utterance's text length (40..120), 0 outside -> LengthRegulator ->
+(acoustic decoder stand-in: first 80 features as the mel) -> HiFi-GAN V1 -> 22.05 kHz waveform.  Random-init
+weights drawn with torch.manual_seed(1234).  One "step" = one pass of the hot path over one batch.  `value`
+counts only VALID audio (sum_b mel_len_b * 256 / 22050), not the padded tail of shorter utterances.
 
-One "step" = one pass of the hot path over one batch.  `value` counts only VALID audio
-(sum_b mel_len_b * 256 / 22050), not the padded tail of shorter utterances.
+Under torchrun (N > 1) every rank runs its own batch (weak scaling, no data-path collective); time = max over
+ranks, value = all ranks' audio / that time.  The default run also measures, outside the headline's timed region
+and reported under `detail.extra`, the other BASELINE.json configs: C1 (B=1, T=200 latency), C3 (JETS shape:
+in_channels 384, GLOBAL batch 64 dealt over the ranks by `plan_shards` = strong scaling, optional NCCL waveform
+gather timed separately), C4 (B=32, T=1000) and the LengthRegulator alone at the bandwidth-regime shape
+(256, 330 -> ~2000, 256).  `--config cN` makes that configuration the printed line instead; `--config c5` is the
+batch x length sweep.
 
-Under torchrun (N > 1) every rank runs its own batch (weak scaling, no data-path collective);
-time = max over ranks, value = all ranks' audio / that time.
-
-`--impl reference` times the reference's algorithm on the host CPU instead (rank 0 only):
-the reference is pure Python and cannot travel to the GPU box, so the arm runs the CPU oracle
-port (oracle/restate.py -- the same torch.nn.functional calls the reference modules make) with
-all host threads, on a bounded sample of the same workload.
+`--impl reference` times the reference's algorithm on the host CPU instead (rank 0 only): the reference is pure
+Python and cannot travel to the GPU box, so the arm runs the CPU oracle port (oracle/restate.py -- the same
+torch.nn.functional calls the reference modules make) with all host threads, on a bounded sample of the same
+workload.  That arm never imports the product package.
 """
 from __future__ import annotations
 
@@ -30,24 +34,43 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "viet-transformer-tts_b200"))
 
 SAMPLE_RATE = 22050
 HOP = 256
-FLOP_PER_FRAME_V1 = 614_105_088  # BASELINE.md section 3 (2*MAC, convs only, in_channels = 80)
+FLOP_PER_FRAME_V1 = 614_105_088          # BASELINE.md section 3 (2*MAC, convs only, in_channels = 80)
+FLOP_PER_FRAME_V1_IN384 = 616_284_160    # in_channels = 384 (JETS), SURVEY 8d
+WORKLOADS = {
+    "c1": "configs[0]: HiFi-GAN V1 on a synthetic 80-bin mel, 200 frames, batch 1, 22.05 kHz",
+    "c2": "configs[1]: LengthRegulator (16,120,256) + HiFi-GAN V1, 22.05 kHz, batch 16/GPU",
+    "c3": "configs[2]: JETS shape: LengthRegulator (64,120,384) + HiFi-GAN V1 (in_channels 384), global batch 64 dealt over the ranks",
+    "c4": "configs[3]: LengthRegulator (32,170,384) -> 1000 frames + HiFi-GAN V1 on (32,80,1000)",
+    "c5": "configs[4]: HiFi-GAN V1 sweep over batch x frames",
+    "lr": "LengthRegulator alone, (256,330,256) -> ~2000 frames (BASELINE.md section 2 shape)",
+}
 
 
-def make_workload(seed: int, B: int = 16, Ttext: int = 120, D: int = 256):
+def make_workload(seed: int, B: int = 16, Ttext: int = 120, D: int = 256, dmax: int = 12):
     """SURVEY.md section 8d, C2 recipe (LR unit-bench variant: ds = randint(1,12) inside length)."""
     import torch
 
     g = torch.Generator().manual_seed(seed)
     hs = torch.randn(B, Ttext, D, generator=g)
-    text_len = torch.randint(40, Ttext + 1, (B,), generator=g)
+    text_len = torch.randint(Ttext // 3, Ttext + 1, (B,), generator=g)
     text_len[0] = Ttext
-    ds = torch.randint(1, 12, (B, Ttext), generator=g)
+    ds = torch.randint(1, dmax, (B, Ttext), generator=g)
     ds[torch.arange(Ttext)[None, :] >= text_len[:, None]] = 0
     return hs, ds
+
+
+def config_of(name: str, hs, ds, B: int) -> dict:
+    """Workload-defining keys only (identical in the GPU arm and the `--impl reference` arm); measurements go to `detail`."""
+    return {
+        "workload": WORKLOADS[name], "batch_per_gpu": B,
+        "padded_mel_frames": int(ds.shape[0] * ds.sum(1).max()), "valid_mel_frames": int(ds.sum()),
+        "value_counts": "valid (unpadded) audio only",
+        "l2": "GPU arm: 256 MiB flush buffer written between timed steps (the per-step activation working set also "
+              "exceeds the 126 MB L2); CPU arm: not applicable",
+    }
 
 
 class ClockSampler:
@@ -111,30 +134,20 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def cpu_oracle_run(hs, ds, sd_folded, n_utts: int, repeats: int):
-    """Time the CPU oracle port on the first `n_utts` utterances.  Returns (audio_s, seconds/run)."""
-    import torch
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+# ---------------------------------------------------------------------------------------------------
+# CPU arms (oracle port).  Nothing here imports vtts_b200.
+# ---------------------------------------------------------------------------------------------------
+def oracle():
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
     import restate
 
-    hs_s, ds_s = hs[:n_utts].clone(), ds[:n_utts].clone()
-    audio = float(ds_s.sum()) * HOP / SAMPLE_RATE
-    times = []
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            frames, _ = restate.lr_expand(hs_s, ds_s.clone())
-            mel = frames[..., :80].transpose(1, 2).contiguous()
-            restate.hifigan_forward(sd_folded, mel)
-            times.append(time.perf_counter() - t0)
-    return audio, times
+    return restate
 
 
 def fold_state_dict(sd):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import restate
-
+    restate = oracle()
     out = {}
     for k, v in sd.items():
         if k.endswith(".weight_g"):
@@ -147,35 +160,60 @@ def fold_state_dict(sd):
     return out
 
 
+def cpu_oracle_run(hs, ds, sd_folded, rows, in_channels: int = 80):
+    """One pass of the CPU oracle port over utterances `rows` (padded among themselves, as the reference's
+    Text2Wav.inference would batch them).  Returns (valid audio seconds, wall seconds)."""
+    import torch
+
+    restate = oracle()
+    hs_s, ds_s = hs[rows].clone(), ds[rows].clone()
+    audio = float(ds_s.sum()) * HOP / SAMPLE_RATE
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        frames, _ = restate.lr_expand(hs_s, ds_s)
+        mel = frames[..., :in_channels].transpose(1, 2).contiguous()
+        restate.hifigan_forward(sd_folded, mel)
+        return audio, time.perf_counter() - t0
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
     import torch
 
-    import vtts_b200
-
+    restate = oracle()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(1234)
-    gen = vtts_b200.HiFiGAN()
-    sd = fold_state_dict(gen.state_dict())
-    hs, ds = make_workload(0)
-    n_utts = args.ref_utts
-    for _ in range(args.warmup):
-        cpu_oracle_run(hs, ds, sd, n_utts, 1)
-    audio, times = cpu_oracle_run(hs, ds, sd, n_utts, args.steps)
-    total = sum(times)
-    value = audio * args.steps / total
-    sample = f"first {n_utts} of 16 utterances per step ({audio:.2f} s audio), fp32, weight-norm pre-folded"
+    name = args.config if args.config in ("c2", "c3", "c4") else "c2"
+    in_ch = 384 if name == "c3" else 80
+    sd = fold_state_dict(restate.make_hifigan_state_dict(in_channels=in_ch, seed=1234))   # same shapes; timing only
+    B = {"c2": args.batch, "c3": 64, "c4": 32}[name]
+    hs, ds = workload_for(name, seed=0, B=B)
+    per_step = max(1, min(args.ref_utts, B))
+    order = list(range(B))
+
+    def rows_of(step):
+        return [order[(step * per_step + i) % B] for i in range(per_step)]
+
+    for w in range(args.warmup):
+        cpu_oracle_run(hs, ds, sd, rows_of(w)[:1], in_ch)
+    audio = secs = 0.0
+    for k in range(args.steps):
+        a, t = cpu_oracle_run(hs, ds, sd, rows_of(k), in_ch)
+        audio += a
+        secs += t
+    value = audio / secs
+    covered = min(B, per_step * args.steps)
+    sample = (f"{per_step} of {B} utterances per step, rotating through the batch ({covered} distinct utterances over "
+              f"{args.steps} steps, {audio:.1f} s audio in total), torch CPU fp32, weight-norm pre-folded; 1 utterance per warm-up step")
     line = {
         "impl": "reference", "metric": "synthesized audio sec/sec (inverse RTF)", "value": value,
         "unit": "audio_s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: LengthRegulator (16,120,256) + HiFi-GAN V1, 22.05 kHz, batch 16/GPU",
-                   "reference_arm": "CPU oracle port of the reference modules, bounded sample"},
+        "config": config_of(name, hs, ds, B),
+        "detail": {"reference_arm": "CPU oracle port of the reference modules (oracle/restate.py), bounded sample per step"},
         "cpu_baseline": {"value": value, "unit": "audio_s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio_s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,24 +222,65 @@ def run_reference(args):
     return 0
 
 
+def workload_for(name: str, seed: int, B: int):
+    if name == "c3":
+        return make_workload(seed, B=B, Ttext=120, D=384)
+    if name == "c4":
+        import torch
+
+        hs, ds = make_workload(seed, B=B, Ttext=170, D=384)
+        # scale the durations so that the longest utterance has exactly max_seq_len = 1000 frames (model_config.yaml:2)
+        longest = int(ds.sum(1).argmax())
+        scale = 1000.0 / float(ds[longest].sum())
+        ds = torch.clamp((ds.float() * scale).floor().long(), min=0)
+        ds[ds.sum(1) == 0, 0] = 1
+        short = 1000 - int(ds[longest].sum())
+        ds[longest, 0] += short
+        return hs, ds
+    return make_workload(seed, B=B)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def cuda_ms(fn, reps, flush=None):
+    """Median milliseconds of fn() over `reps` CUDA-event-timed calls (L2 flushed before each when `flush` is given)."""
+    import torch
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        if flush is not None:
+            flush.fill_(3)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=None, choices=[None, "fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--ref-utts", type=int, default=2, help="utterances per step for the CPU arms")
+    ap.add_argument("--ref-utts", type=int, default=4, help="utterances per step for the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN) timing of the module tree")
     ap.add_argument("--no-trim", action="store_true", help="process the padded tail of short utterances too")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / C4 / LR-large measurements of the default run")
+    ap.add_argument("--gather", action="store_true", help="C3: time the optional NCCL waveform gather as well")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
         return run_reference(args)
 
+    sys.path.insert(0, os.path.join(ROOT, "viet-transformer-tts_b200"))
     import torch
 
     import vtts_b200
@@ -220,116 +299,275 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     precision = args.precision or vtts_b200.hifigan.DEFAULT_PRECISION
-    torch.manual_seed(1234)  # config/train_config.yaml:1 -- identical weights on every rank
-    gen = vtts_b200.HiFiGAN()
-    gen.precision = precision
-    gen = gen.to(dev).eval()
-    lr = vtts_b200.LengthRegulator()
-    synth = vtts_b200.Synthesizer(gen, lr, trim_padding=not args.no_trim)
-
-    hs, ds = make_workload(seed=rank, B=args.batch)
-    hs_pin, ds_pin = hs.pin_memory(), ds.pin_memory()
-    hs_d, ds_d = hs.to(dev), ds.to(dev)
-    valid_frames = int(ds.sum())
-    audio_s = valid_frames * HOP / SAMPLE_RATE
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    lr = vtts_b200.LengthRegulator()
 
-    trim = not args.no_trim and precision != "fp32"
-
-    def run_gen(mel, mel_len):
-        return gen.forward_trimmed(mel, mel_len) if trim else gen(mel)
-
-    def step_device():
-        frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
-        mel = frames[..., :80].transpose(1, 2)
-        wav = run_gen(mel, mel_len)
-        return frames, wav
-
-    def step_generator_only(mel):
-        return gen(mel)
+    def make_gen(in_channels=80):
+        torch.manual_seed(1234)  # config/train_config.yaml:1 -- identical weights on every rank
+        g = vtts_b200.HiFiGAN(in_channels=in_channels)
+        g.precision = precision
+        return g.to(dev).eval()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            frames, wav = step_device()
-            synth(hs_pin, ds_pin)
-        torch.cuda.synchronize(dev)
-        T_out = frames.shape[1]
-        padded_frames = frames.shape[0] * T_out
-        launches_per_step = 2 + gen.last_launch_count
+    def reduce_stats(ms_total: float, audio_s: float):
+        """max over ranks of the timed region, sum of audio, per-rank spread (names a straggler)."""
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        a = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+        per_rank = [ms_total]
+        if dist is not None:
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank = [float(x.item()) for x in allt]
+            dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        s = sorted(per_rank)
+        return max(per_rank), float(a.item()), {"min": s[0], "median": s[len(s) // 2], "max": s[-1],
+                                                "slowest_rank": per_rank.index(s[-1])}
 
-        # ---- device-resident timing: K steps, L2 flushed between steps (outside the events) ----
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
-        with ClockSampler(local) as clocks:
-            for k in range(args.steps):
-                flush.fill_(k & 0xFF)
-                ev[k][0].record()
-                frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
-                mel = frames[..., :80].transpose(1, 2)
-                gev[k][0].record()
-                wav = run_gen(mel, mel_len)
-                gev[k][1].record()
-                ev[k][1].record()
+    trim = not args.no_trim and precision != "fp32"
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6547.5)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+
+    # ------------------------------------------------------------------------------------------
+    # building blocks
+    # ------------------------------------------------------------------------------------------
+    def time_path(gen, hs, ds, steps, warmup, in_ch):
+        """K device-timed steps of LR -> stand-in decoder -> generator on resident inputs."""
+        hs_d, ds_d = hs.to(dev), ds.to(dev)
+
+        def step():
+            frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
+            mel = frames[..., :in_ch].transpose(1, 2)
+            wav = gen.forward_trimmed(mel, mel_len) if trim else gen(mel)
+            return frames, mel_len, wav
+
+        with torch.no_grad():
+            for _ in range(warmup):
+                frames, mel_len, wav = step()
+            torch.cuda.synchronize(dev)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
             barrier()
+            with ClockSampler(local) as clocks:
+                for k in range(steps):
+                    flush.fill_(k & 0xFF)
+                    ev[k][0].record()
+                    frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
+                    mel = frames[..., :in_ch].transpose(1, 2)
+                    gev[k][0].record()
+                    wav = gen.forward_trimmed(mel, mel_len) if trim else gen(mel)
+                    gev[k][1].record()
+                    ev[k][1].record()
+                barrier()
         step_ms = [a.elapsed_time(b) for a, b in ev]
         gen_ms = [a.elapsed_time(b) for a, b in gev]
-        total_ms = sum(step_ms)
+        return {"total_ms": sum(step_ms), "gen_ms": sum(gen_ms) / len(gen_ms), "frames": frames, "mel_len": mel_len, "wav": wav,
+                "clocks": clocks.summary(), "launches": 2 + gen.last_launch_count}
 
-        # transparency: the same generator pass WITHOUT the padding trim (module-level forward, strict parity)
-        uev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 5))]
-        mel_full = frames[..., :80].transpose(1, 2)
-        for a_, b_ in uev:
-            flush.fill_(1)
-            a_.record()
-            gen(mel_full)
-            b_.record()
-        torch.cuda.synchronize(dev)
-        untrimmed_ms = sum(a_.elapsed_time(b_) for a_, b_ in uev) / len(uev)
+    def time_e2e(synth, hs_pin, ds_pin, steps):
+        """The same metric through Synthesizer with HOST buffers: H2D of the inputs and D2H of the waveform inside."""
+        with torch.no_grad():
+            e2e_ms = []
+            barrier()
+            for k in range(steps):
+                flush.fill_(k & 0xFF)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                synth(hs_pin, ds_pin)  # synchronises before returning
+                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+            barrier()
+            sync_total = sum(e2e_ms)
+            for _ in range(2):
+                synth.submit(hs_pin, ds_pin).result()
+            torch.cuda.synchronize(dev)
+            barrier()
+            t0 = time.perf_counter()
+            pending = None
+            for k in range(steps):
+                nxt = synth.submit(hs_pin, ds_pin)
+                if pending is not None:
+                    pending.result()
+                pending = nxt
+            wav_h, _ = pending.result()
+            pipe_total = 1e3 * (time.perf_counter() - t0)
+            barrier()
+        return pipe_total, sync_total, wav_h
 
-        # LengthRegulator alone (HBM-bandwidth class, launch-latency bound at these sizes): kernels only
-        # (max_len given -> no host read), algorithmic bytes = xs + ds read, frames + mel_len written
-        lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-        for a_, b_ in lev:
-            flush.fill_(2)
-            a_.record()
-            lr.forward_with_lengths(hs_d, ds_d, max_len=T_out)
-            b_.record()
-        torch.cuda.synchronize(dev)
-        lr_us = sorted(1e3 * a_.elapsed_time(b_) for a_, b_ in lev)[len(lev) // 2]
-        lr_bytes = hs_d.numel() * 4 + ds_d.numel() * 8 + frames.numel() * 4 + ds_d.shape[0] * 8
-        # single-utterance latency at configs[0] (B=1, T=200 frames = 2.3 s of audio): blocking module call, wall clock
+    def lr_alone(hs, ds, reps=7):
+        hs_d, ds_d = hs.to(dev), ds.to(dev)
+        with torch.no_grad():
+            frames, _ = lr.forward_with_lengths(hs_d, ds_d)
+            T_out = frames.shape[1]
+            us = 1e3 * cuda_ms(lambda: lr.forward_with_lengths(hs_d, ds_d, max_len=T_out), reps, flush)
+        nbytes = hs_d.numel() * 4 + ds_d.numel() * 8 + frames.numel() * 4 + ds_d.shape[0] * 8
+        return {"shape": [list(hs.shape), int(T_out)], "us": us, "algorithmic_bytes": nbytes, "GBps": nbytes / (us * 1e-6) / 1e9,
+                "frac_of_hbm_peak": nbytes / (us * 1e-6) / 1e9 / hbm_peak,
+                "note": "kernels only (rowsum + gather), output length supplied; bytes = xs + ds read, frames + mel_len written"}
+
+    def latency_c1(gen):
         mel1 = torch.randn(1, 80, 200, device=dev)
-        for _ in range(3):
-            gen(mel1)
-        torch.cuda.synchronize(dev)
-        lat = []
-        for _ in range(10):
-            t0 = time.perf_counter()
-            gen(mel1)
+        with torch.no_grad():
+            for _ in range(3):
+                gen(mel1)
             torch.cuda.synchronize(dev)
-            lat.append(1e3 * (time.perf_counter() - t0))
-        lat.sort()
-        gf = gen.graphed(mel1)                    # the same forward replayed from a CUDA graph (no per-launch host cost)
-        for _ in range(3):
-            gf(mel1)
-        torch.cuda.synchronize(dev)
-        lat_g = []
-        for _ in range(10):
-            t0 = time.perf_counter()
-            gf(mel1)
+            lat = []
+            for _ in range(10):
+                t0 = time.perf_counter()
+                gen(mel1)
+                torch.cuda.synchronize(dev)
+                lat.append(1e3 * (time.perf_counter() - t0))
+            lat.sort()
+            gf = gen.graphed(mel1)   # the same forward replayed from a CUDA graph (no per-launch host cost)
+            for _ in range(3):
+                gf(mel1)
             torch.cuda.synchronize(dev)
-            lat_g.append(1e3 * (time.perf_counter() - t0))
-        lat_g.sort()
+            lat_g = []
+            for _ in range(10):
+                t0 = time.perf_counter()
+                gf(mel1)
+                torch.cuda.synchronize(dev)
+                lat_g.append(1e3 * (time.perf_counter() - t0))
+            lat_g.sort()
+        audio = 200 * HOP / SAMPLE_RATE
+        return {"median_ms": lat[len(lat) // 2], "min_ms": lat[0], "cuda_graph_median_ms": lat_g[len(lat_g) // 2],
+                "audio_s_per_s": audio / (lat[len(lat) // 2] * 1e-3), "audio_s_per_s_graph": audio / (lat_g[len(lat_g) // 2] * 1e-3),
+                "launches": gen.last_launch_count,
+                "note": "HiFiGAN.forward on (1,80,200), blocking, wall clock; cuda_graph = HiFiGAN.graphed() replay of the same launches"}
 
+    def run_c3(steps):
+        """Strong scaling: ONE global batch of 64 utterances dealt over the ranks by plan_shards (longest first, snake)."""
+        gen3 = make_gen(in_channels=384)
+        hs, ds = workload_for("c3", seed=0, B=64)
+        lens = ds.sum(1).tolist()
+        idx = vtts_b200.plan_shards(lens, world)[rank]
+        sel = torch.as_tensor(idx, dtype=torch.long)
+        r = time_path(gen3, hs[sel], ds[sel], steps, 3, 384)
+        worst, _, spread = reduce_stats(r["total_ms"], 0.0)
+        audio = float(ds.sum()) * HOP / SAMPLE_RATE
+        out = {"workload": WORKLOADS["c3"], "scaling": "strong", "global_batch": 64, "ranks": world, "rows_this_rank": len(idx),
+               "ms_per_step": worst / steps, "audio_s_per_s": audio * steps / (worst * 1e-3), "per_rank_total_ms": spread,
+               "frames_per_rank_padded": int(r["frames"].shape[0] * r["frames"].shape[1]),
+               "tflops": float(ds.sum()) * FLOP_PER_FRAME_V1_IN384 * steps / (worst * 1e-3) / 1e12 / world}
+        if world > 1 and args.gather:
+            wav_len = r["mel_len"] * gen3.upsample_factor
+            barrier()
+            t0 = time.perf_counter()
+            vtts_b200.gather_waveforms(r["wav"], wav_len, idx, 64)
+            barrier()
+            out["gather_ms"] = 1e3 * (time.perf_counter() - t0)
+            out["gather_note"] = "optional final exchange: four all_gather calls over NCCL, padded to the global maximum"
+        del gen3
+        return out
+
+    def run_c4(steps):
+        gen = make_gen()
+        hs, ds = workload_for("c4", seed=rank, B=32)
+        r = time_path(gen, hs, ds, steps, 3, 80)
+        lr_c4 = lr_alone(hs, ds)
+        audio = float(ds.sum()) * HOP / SAMPLE_RATE
+        with torch.no_grad():
+            mel = torch.randn(32, 80, 1000, device=dev)
+            full_ms = cuda_ms(lambda: gen(mel), 3, flush)
+        out = {"workload": WORKLOADS["c4"], "ms_per_step": r["total_ms"] / steps, "audio_s_per_s": audio * steps / (r["total_ms"] * 1e-3),
+               "valid_mel_frames": int(ds.sum()), "padded_mel_frames": 32 * 1000, "generator_ms_untrimmed_32x1000": full_ms,
+               "untrimmed_tflops": 32000 * FLOP_PER_FRAME_V1 / (full_ms * 1e-3) / 1e12, "length_regulator": lr_c4}
+        del gen
+        return out
+
+    def run_c5():
+        gen = make_gen()
+        grid = []
+        with torch.no_grad():
+            for B in (1, 4, 16, 64, 256):
+                for T in (100, 500, 2000):
+                    if B * T > 128_000:     # 256 x 2000 needs 16.8 GB per fp32 stage tensor: out of the sweep on one GPU
+                        grid.append({"batch": B, "frames": T, "skipped": "B*T > 128k frames on one GPU"})
+                        continue
+                    mel = torch.randn(B, 80, T, device=dev)
+                    for _ in range(2):
+                        gen(mel)
+                    ms = cuda_ms(lambda: gen(mel), 3, flush)
+                    grid.append({"batch": B, "frames": T, "ms": ms, "audio_s_per_s": B * T * HOP / SAMPLE_RATE / (ms * 1e-3),
+                                 "tflops": B * T * FLOP_PER_FRAME_V1 / (ms * 1e-3) / 1e12})
+                    del mel
+        return {"workload": WORKLOADS["c5"], "per_gpu": True, "grid": grid}
+
+    # ------------------------------------------------------------------------------------------
+    # secondary configurations as the printed line
+    # ------------------------------------------------------------------------------------------
+    if args.config in ("c3", "c4", "c5", "lr", "c1"):
+        if args.config == "c3":
+            res = run_c3(args.steps)
+            value, ms = res["audio_s_per_s"], res["ms_per_step"]
+            hs, ds = workload_for("c3", 0, 64)
+            cfg, scaling = config_of("c3", hs, ds, 64 // world), "strong"
+        elif args.config == "c4":
+            res = run_c4(args.steps)
+            hs, ds = workload_for("c4", rank, 32)
+            _, audio_all, _ = reduce_stats(0.0, float(ds.sum()) * HOP / SAMPLE_RATE)
+            worst, _, _ = reduce_stats(res["ms_per_step"], 0.0)
+            value, ms = audio_all / (worst * 1e-3), worst
+            cfg, scaling = config_of("c4", hs, ds, 32), "weak"
+        elif args.config == "c5":
+            res = run_c5()
+            best = max((g for g in res["grid"] if "ms" in g), key=lambda g: g["audio_s_per_s"])
+            value, ms, scaling = best["audio_s_per_s"], best["ms"], "weak"
+            cfg = {"workload": WORKLOADS["c5"], "value_is": f"best cell: batch {best['batch']} x {best['frames']} frames, one GPU"}
+        elif args.config == "lr":
+            hs, ds = make_workload(rank, B=256, Ttext=330, D=256, dmax=13)
+            res = lr_alone(hs, ds, reps=max(5, args.steps))
+            value, ms, scaling = float(ds.sum()) * HOP / SAMPLE_RATE / (res["us"] * 1e-6), res["us"] * 1e-3, "weak"
+            cfg = config_of("lr", hs, ds, 256)
+        else:
+            res = latency_c1(make_gen())
+            value, ms, scaling = res["audio_s_per_s"], res["median_ms"], "weak"
+            cfg = {"workload": WORKLOADS["c1"]}
+        if rank == 0:
+            line = {"metric": "synthesized audio sec/sec (inverse RTF)", "value": value, "unit": "audio_s/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
+                    "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
+                    "config": cfg, "detail": res}
+            if args.config == "lr":
+                line["roofline"] = {"bound": "hbm", "achieved": res["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": res["frac_of_hbm_peak"], "traffic": None, "kernel": "lr_rowsum_kernel + lr_gather_kernel"}
+            print(json.dumps(line))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------------------------------
+    # headline: C2
+    # ------------------------------------------------------------------------------------------
+    gen = make_gen()
+    synth = vtts_b200.Synthesizer(gen, lr, trim_padding=not args.no_trim)
+    hs, ds = make_workload(seed=rank, B=args.batch)
+    hs_pin, ds_pin = hs.pin_memory(), ds.pin_memory()
+    valid_frames = int(ds.sum())
+    audio_s = valid_frames * HOP / SAMPLE_RATE
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            synth(hs_pin, ds_pin)
+    r = time_path(gen, hs, ds, args.steps, args.warmup, 80)
+    frames = r["frames"]
+    T_out = frames.shape[1]
+    padded_frames = frames.shape[0] * T_out
+
+    with torch.no_grad():
+        # transparency: the same generator pass WITHOUT the padding trim (module-level forward, strict parity)
+        mel_full = frames[..., :80].transpose(1, 2)
+        untrimmed_ms = cuda_ms(lambda: gen(mel_full), min(args.steps, 5), flush)
         # context (SURVEY 8d "the real bar"): the same nn.Module tree run eagerly by PyTorch/cuDNN on this GPU -- what the
-        # reference's own modules do on a B200.  This is the shells' autograd/eager path (hifigan.py:_forward_eager),
-        # outside every timed region above; rank 0 only.
+        # reference's own modules do on a B200.  Outside every timed region above; rank 0 only.
         eager = None
         if rank == 0 and not args.no_eager_baseline:
             eager = {}
@@ -339,117 +577,81 @@ def main():
                 torch.backends.cuda.matmul.allow_tf32 = tf32
                 for _ in range(2):
                     gen._forward_eager(mel_full)
-                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
-                for a_, b_ in ev:
-                    a_.record()
-                    gen._forward_eager(mel_full)
-                    b_.record()
-                torch.cuda.synchronize(dev)
-                ms = sorted(a_.elapsed_time(b_) for a_, b_ in ev)[1]
-                eager[f"generator_ms_{name}"] = ms
+                eager[f"generator_ms_{name}"] = cuda_ms(lambda: gen._forward_eager(mel_full), 3)
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
-            eager["note"] = ("PyTorch eager (cuDNN) forward of the same module tree, padded batch, no trim; compare with "
-                             "config.generator_ms_untrimmed")
+            eager["ours_generator_ms_untrimmed"] = untrimmed_ms
+            eager["speedup_vs_tf32"] = eager["generator_ms_tf32"] / untrimmed_ms
+            eager["note"] = ("PyTorch eager (cuDNN) forward of the same module tree on this GPU, padded batch (16 x %d frames), "
+                             "no trim; ours = the untrimmed kernel forward on the same input" % T_out)
+    e2e_total, e2e_sync_total, wav_h = time_e2e(synth, hs_pin, ds_pin, args.steps)
 
-        # ---- end-to-end through the public API with host buffers (H2D + D2H inside) -------------
-        e2e_ms = []
-        barrier()
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            wav_h, wav_len_h = synth(hs_pin, ds_pin)  # synchronises before returning
-            e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        barrier()
-        e2e_sync_total = sum(e2e_ms)
-        # pipelined form (Synthesizer.submit): same per-step host->device inputs and device->host waveform, but the
-        # read-back of step k runs on a copy stream behind the kernels of step k+1.  No L2 flush inside this region
-        # (it cannot be excluded from the clock here); the per-step working set is far larger than L2 anyway.
-        for _ in range(2):
-            synth.submit(hs_pin, ds_pin).result()
-        torch.cuda.synchronize(dev)
-        barrier()
-        t0 = time.perf_counter()
-        pending = None
-        for k in range(args.steps):
-            nxt = synth.submit(hs_pin, ds_pin)
-            if pending is not None:
-                wav_h, wav_len_h = pending.result()
-            pending = nxt
-        wav_h, wav_len_h = pending.result()
-        e2e_total = 1e3 * (time.perf_counter() - t0)
-        barrier()
+    total_ms_all, audio_all, spread = reduce_stats(r["total_ms"], audio_s)
+    e2e_ms_all, _, _ = reduce_stats(e2e_total, 0.0)
+    e2e_sync_ms_all, _, _ = reduce_stats(e2e_sync_total, 0.0)
 
-    t = torch.tensor([total_ms, e2e_total, e2e_sync_total], dtype=torch.float64, device=dev)
-    a = torch.tensor([audio_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(a, op=dist.ReduceOp.SUM)
-    total_ms_all, e2e_ms_all, e2e_sync_ms_all = t.tolist()
-    audio_all = float(a.item())
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra["c1"] = latency_c1(gen) if rank == 0 else None
+            hs_l, ds_l = make_workload(rank, B=256, Ttext=330, D=256, dmax=13)
+            extra["lr_large"] = lr_alone(hs_l, ds_l)
+            extra["lr_c2"] = lr_alone(hs, ds)
+            del hs_l, ds_l
+            extra["c4"] = run_c4(3)
+            extra["c3"] = run_c3(3)
+        except Exception as e:  # the headline must survive a failure in the side measurements
+            extra["error"] = repr(e)
 
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except Exception:
-            pass
-        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
-        gen_avg_ms = sum(gen_ms) / len(gen_ms)
-        margin = gen.TRIM_MARGIN_FRAMES
-        # algorithmic work of the trimmed step = the valid frames only (the few look-ahead frames per utterance that
-        # the kernels still compute behind mel_len are overhead, not counted)
+        gen_avg_ms = r["gen_ms"]
+        # algorithmic work of the trimmed step = the valid frames only (the look-ahead frames the kernels still compute behind
+        # mel_len are overhead, not counted)
         needed_frames = valid_frames if trim else padded_frames
         flops = needed_frames * FLOP_PER_FRAME_V1
         achieved = flops / (gen_avg_ms * 1e-3) / 1e12
-        # DRAM bytes of the same launch set: ncu launch list of the untrimmed forward at this shape (profiles/), scaled by
-        # the fraction of frames the trimmed step computes (traffic is proportional to the tiles processed)
         traffic_bytes, traffic_note = None, "no ncu capture committed"
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                tj = json.load(fh)
-            traffic_bytes = tj["dram_bytes_per_forward"] * needed_frames / float(16 * 759)
-            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum over the 52 launches of one forward "
-                            "(profiles/r01_launch_list.csv, B=16 x 759 frames untrimmed), scaled by frames computed / 12144")
-        except Exception:
-            pass
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tf)) as fh:
+                    tj = json.load(fh)
+                traffic_bytes = tj["dram_bytes_per_forward"] * needed_frames / float(16 * 759)
+                traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum over the {tj.get('launches', '?')} launches of one "
+                                f"forward (profiles/{tf}, B=16 x 759 frames untrimmed), scaled by frames computed / 12144")
+                break
+            except Exception:
+                continue
         value = audio_all * args.steps / (total_ms_all * 1e-3)
+        cfg = config_of("c2", hs, ds, args.batch)
         line = {
             "metric": "synthesized audio sec/sec (inverse RTF)", "value": value, "unit": "audio_s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
-            "config": {
-                "workload": "configs[1]: LengthRegulator (16,120,256) + HiFi-GAN V1, 22.05 kHz, batch 16/GPU",
-                "precision": precision, "batch_per_gpu": args.batch, "padded_mel_frames": padded_frames,
-                "valid_mel_frames": valid_frames, "l2": "256 MiB flush buffer written between timed steps; "
-                "per-step activation working set also exceeds the 126 MB L2",
-                "value_counts": "valid (unpadded) audio only",
-                "padding_trim": (f"on: generator tiles beyond mel_len + per-layer receptive-field margin (<= {margin} frames) "
-                                 "skipped (valid samples bit-identical, tests/test_tc_gpu.py)" if trim else "off"),
+            "config": cfg,
+            "detail": {
+                "precision": precision,
+                "padding_trim": ("on: every layer computes mel_len frames plus the look-ahead its successors need (derived from the "
+                                 "kernel sizes / dilations / scales); valid samples bit-identical to the untrimmed call "
+                                 "(tests/test_tc_gpu.py)" if trim else "off"),
                 "frames_needed_for_roofline": needed_frames,
+                "generator_ms": gen_avg_ms,
                 "generator_ms_untrimmed": untrimmed_ms,
                 "untrimmed_generator_tflops": padded_frames * FLOP_PER_FRAME_V1 / (untrimmed_ms * 1e-3) / 1e12,
-                "torch_eager_gpu": eager,
-                "length_regulator": {"us": lr_us, "algorithmic_bytes": lr_bytes, "GBps": lr_bytes / (lr_us * 1e-6) / 1e9,
-                                     "note": "kernels only (rowsum + gather), output length supplied; launch-latency bound"},
-                "latency_ms_configs0_b1_t200": {"median": lat[len(lat) // 2], "min": lat[0],
-                                                "cuda_graph_median": lat_g[len(lat_g) // 2],
-                                                "note": "HiFiGAN.forward on (1,80,200), blocking, wall clock; cuda_graph = "
-                                                        "HiFiGAN.graphed() replay of the same launches"},
+                "untrimmed_audio_s_per_s_valid": audio_s / (untrimmed_ms * 1e-3),
+                "per_rank_total_ms": spread,
+                "extra": extra,
             },
-            "clocks": clocks.summary(),
+            "gpu_eager_baseline": eager,
+            "clocks": r["clocks"],
             "e2e": {"value": audio_all * args.steps / (e2e_ms_all * 1e-3), "unit": "audio_s/s",
                     "h2d_bytes_per_step": hs.numel() * 4 + ds.numel() * 8,
-                    "d2h_bytes_per_step": int(wav.numel()) * 4 + ds.shape[0] * 8,
+                    "d2h_bytes_per_step": int(wav_h.numel()) * 4 + ds.shape[0] * 8,
                     "ms_per_step": e2e_ms_all / args.steps,
                     "mode": "Synthesizer.submit(): read-back of step k overlaps the kernels of step k+1; every step's "
                             "inputs and waveform cross PCIe inside the timed region",
                     "sync_value": audio_all * args.steps / (e2e_sync_ms_all * 1e-3),
                     "sync_note": "Synthesizer.__call__(): one blocking call per step (H2D, kernels, D2H, sync)"},
-            "gpu_launches": launches_per_step * args.steps * world,
+            "gpu_launches": r["launches"] * args.steps * world,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                          "frac": achieved / tc_peak, "traffic": traffic_bytes,
                          "kernel": "generator conv kernels (all launches of one forward)",
@@ -460,12 +662,13 @@ def main():
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             sd = fold_state_dict(gen.state_dict())
-            cpu_oracle_run(hs, ds, sd, 1, 1)  # warm-up
-            caudio, ctimes = cpu_oracle_run(hs, ds, sd, args.ref_utts, 3)
-            ctimes.sort()
+            cpu_oracle_run(hs, ds, sd, [0], 80)  # warm-up
+            rows = list(range(min(args.ref_utts, args.batch)))
+            runs = sorted((cpu_oracle_run(hs, ds, sd, rows, 80) for _ in range(3)), key=lambda x: x[1])
+            caudio, csec = runs[1]
             line["cpu_baseline"] = {
-                "value": caudio / ctimes[len(ctimes) // 2], "unit": "audio_s/s", "cores": cores, "kind": "port",
-                "sample": f"first {args.ref_utts} of {args.batch} utterances ({caudio:.2f} s audio), median of 3, "
+                "value": caudio / csec, "unit": "audio_s/s", "cores": cores, "kind": "port",
+                "sample": f"first {len(rows)} of {args.batch} utterances ({caudio:.2f} s audio), median of 3, "
                           "CPU oracle port (torch fp32, weight-norm pre-folded)",
             }
         print(json.dumps(line))
