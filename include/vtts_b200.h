@@ -172,6 +172,13 @@ int vtts_gen_forward(VttsGen *h, const float *c, const float *g, float *wav, int
  * valid until the forward has run. */
 int vtts_gen_set_valid_lengths(VttsGen *h, const int64_t *mel_len, int margin_frames);
 
+/* Diagnostic for the 16-bit paths (not in the reference): activation range probe.  absmax (device, vtts_gen_num_layers + 1
+ * floats zeroed by the caller, or NULL to disable): until reset, the FP32 path of vtts_gen_forward records
+ * absmax[l] = max |output of layer l| (after the residual add, i.e. the tensor whose LeakyReLU the next conv consumes) and
+ * absmax[num_layers] = max |c|.  These are exactly the tensors the 16-bit paths round to fp16 / bf16 operands
+ * (cvt.rn.satfinite clips silently at 65504 for fp16): a checkpoint whose probe stays below 65504 cannot saturate. */
+int vtts_gen_set_range_probe(VttsGen *h, float *absmax);
+
 /* Number of kernel launches the last vtts_gen_forward on this handle issued. */
 int vtts_gen_last_launch_count(const VttsGen *h);
 

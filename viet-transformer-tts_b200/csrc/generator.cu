@@ -164,6 +164,14 @@ extern "C" int vtts_gen_load_layer(VttsGen *h, int layer, const float *weight_v,
 // --------------------------------------------------------------------------------------------
 namespace {
 
+// max |x| over n floats, folded into *out (non-negative floats order like their bit patterns)
+__global__ void absmax_kernel(const float *__restrict__ x, size_t n, float *out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+}
+
 struct Plan {
     std::vector<int> C, L;  // per stage, after upsample
     size_t max_elems = 0;
@@ -210,6 +218,14 @@ static int forward_fp32(VttsGen *h, const float *c, const float *g, float *wav, 
         return VTTS_OK;
     };
 
+    // optional range probe (vtts_gen_set_range_probe): max |layer output| per layer
+    auto probe = [&](int layer, const float *y, size_t n) {
+        if (!h->range_probe || n == 0) return;
+        size_t blocks = (n + 1023) / 1024;
+        if (blocks > 1184) blocks = 1184;
+        absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, n, h->range_probe + layer);
+    };
+    probe((int)h->layers.size(), c, (size_t)B * cfg.in_channels * T);
     // global conditioning: c += global_conv(g)  (generator.py:146-147) -> per-batch bias
     const float *bias_b = nullptr;
     if (g) {
@@ -225,6 +241,7 @@ static int forward_fp32(VttsGen *h, const float *c, const float *g, float *wav, 
         p.bias_b = bias_b;
         if ((rc = launch_conv_fp32(p, st))) return rc;
         h->launch_count++;
+        probe(h->idx_pre, P, (size_t)B * cfg.channels * T);
         if ((rc = dump(0, P, cfg.channels, T))) return rc;
     }
     const float *cur = P;
@@ -242,6 +259,7 @@ static int forward_fp32(VttsGen *h, const float *c, const float *g, float *wav, 
             p.n_pos = L + p.taps - 1; p.slope_in = cfg.lrelu_slope;
             if ((rc = launch_conv_fp32(p, st))) return rc;
             h->launch_count++;
+            probe(h->idx_up[i], U, (size_t)B * C * Lo);
             if ((rc = dump(2 * i + 1, U, C, Lo))) return rc;
         }
         for (int j = 0; j < cfg.num_blocks; ++j) {
@@ -257,6 +275,7 @@ static int forward_fp32(VttsGen *h, const float *c, const float *g, float *wav, 
                 if (cfg.use_additional_convs) {
                     if ((rc = launch_conv_fp32(p1, st))) return rc;
                     h->launch_count++;
+                    probe(h->idx_c1[i][j][m], Tt, (size_t)B * C * Lo);
                     p2 = conv_params(h->layers[h->idx_c2[i][j][m]], Tt, ynew, B, Lo, cfg.lrelu_slope);
                     fin = &p2;
                 }
@@ -267,6 +286,8 @@ static int forward_fp32(VttsGen *h, const float *c, const float *g, float *wav, 
                 }
                 if ((rc = launch_conv_fp32(*fin, st))) return rc;
                 h->launch_count++;
+                // (the last unit of a block writes the running MRF sum: an upper bound of the block output's range / num_blocks)
+                probe(cfg.use_additional_convs ? h->idx_c2[i][j][m] : h->idx_c1[i][j][m], ynew, (size_t)B * C * Lo);
                 y = ynew;
             }
         }
@@ -318,6 +339,12 @@ extern "C" int vtts_gen_set_valid_lengths(VttsGen *h, const int64_t *mel_len, in
     if (margin_frames < 0) margin_frames = 0;   // auto: the per-layer margins derived from the receptive fields
     h->trim_lens = mel_len;
     h->trim_margin = margin_frames;
+    return VTTS_OK;
+}
+
+extern "C" int vtts_gen_set_range_probe(VttsGen *h, float *absmax) {
+    VTTS_REQUIRE(h, "vtts_gen_set_range_probe: null handle");
+    h->range_probe = absmax;
     return VTTS_OK;
 }
 

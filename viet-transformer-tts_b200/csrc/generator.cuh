@@ -63,6 +63,7 @@ struct VttsGen {
     const int64_t *trim_lens = nullptr;  // device (B) valid mel frames for the NEXT forward (vtts_gen_set_valid_lengths)
     int trim_margin = 0;
     std::vector<vtts::tc::ChainWeights> chain;   // [stage * num_blocks + block], packed lazily by tc_forward
+    float *range_probe = nullptr;                // device (num_layers + 1) floats or null (vtts_gen_set_range_probe)
     bool chain_dirty = true;                     // a layer was (re)loaded since the last packing
 };
 

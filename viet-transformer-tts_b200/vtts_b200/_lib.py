@@ -59,6 +59,7 @@ SIGNATURES = {
                                    C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vtts_gen_set_valid_lengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vtts_gen_last_launch_count": (C.c_int, [C.c_void_p]),
+    "vtts_gen_set_range_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vtts_dbg_conv1d_fp32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "vtts_dbg_conv1d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

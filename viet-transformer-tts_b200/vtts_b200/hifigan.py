@@ -305,6 +305,35 @@ class _GeneratorBase(nn.Module):
         graph.  ``c`` / ``g`` / ``lengths`` are examples that fix shapes and dtypes; see :class:`GraphedForward`."""
         return GraphedForward(self, c, g, lengths)
 
+    FP16_MAX = 65504.0
+
+    def activation_range(self, c: torch.Tensor, g: Optional[torch.Tensor] = None) -> dict:
+        """Diagnostic for the 16-bit paths: run ``c`` through the fp32 kernels and report ``max |x|`` of every tensor the
+        16-bit paths round to 16-bit operands (the input and every conv layer's output after its residual add).
+
+        Returns ``{"layers": [max_abs per layer, library order], "input": max |c|, "max": overall max,
+        "fp16_headroom": 65504 / max}``.  fp16 operands (``precision = "fp16"``, the default) clip silently at 65504
+        (``cvt.rn.satfinite``): a checkpoint / input distribution with ``fp16_headroom`` comfortably above 1 cannot
+        saturate; below 1 use ``precision = "bf16"`` or ``"fp32"``.  Synthesis-time check, not part of the hot path.
+        """
+        lib = _lib.load()
+        dev = c.device
+        with torch.cuda.device(dev):
+            h = self._handle(dev)
+            n = _lib.check(lib.vtts_gen_num_layers(h))
+            probe = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+            saved = self.precision
+            _lib.check(lib.vtts_gen_set_range_probe(h, probe.data_ptr()))
+            try:
+                self.precision = "fp32"
+                self._run_kernels(c, g)
+            finally:
+                self.precision = saved
+                lib.vtts_gen_set_range_probe(h, None)
+            vals = probe.cpu().tolist()
+        mx = max(vals)
+        return {"layers": vals[:n], "input": vals[n], "max": mx, "fp16_headroom": self.FP16_MAX / mx if mx > 0 else float("inf")}
+
     def debug_stage(self, c: torch.Tensor, stage: int, g: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Test hook: intermediate tensor (B, C, L) fp32 of the kernel path (see vtts_gen_forward)."""
         return self._run_kernels(c, g, dump_stage=stage)[1]
