@@ -484,6 +484,36 @@ def main():
         del gen
         return out
 
+    def run_c2_tail(hs, ds):
+        """C2 with the FastSpeech2 tail in the path: regulator -> 4-layer / 256-hidden decoder + Postnet (conv kernels,
+        vtts_b200.AcousticTail, random init) -> vocoder, on resident inputs; the headline keeps the slice stand-in so that it
+        stays comparable with round 1 and with the reference arm."""
+        cfg = {"decoder_head": 2, "conv_filter_size": 1024, "conv_kernel_size": [9, 1], "decoder_dropout": 0.2}
+        torch.manual_seed(1234)
+        tail = vtts_b200.AcousticTail(vtts_b200.Decoder(4, 256, 1000, cfg), torch.nn.Linear(256, 80),
+                                      vtts_b200.Postnet(80, {"embedding_dim": 512, "conv_layers": 5, "kernel_size": 5})).to(dev).eval()
+        gen = make_gen()
+        hs_d, ds_d = hs.to(dev), ds.to(dev)
+
+        def step():
+            frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
+            mel = tail(frames, mel_len)
+            return gen.forward_trimmed(mel, mel_len) if trim else gen(mel)
+
+        def tail_only():
+            frames, mel_len = lr.forward_with_lengths(hs_d, ds_d)
+            return tail(frames, mel_len)
+
+        with torch.no_grad():
+            for _ in range(3):
+                step()
+            ms = cuda_ms(step, 5, flush)
+            ms_tail = cuda_ms(tail_only, 5, flush)
+        audio = float(ds.sum()) * HOP / SAMPLE_RATE
+        del gen, tail
+        return {"ms_per_step": ms, "audio_s_per_s": audio / (ms * 1e-3), "regulator_plus_tail_ms": ms_tail,
+                "note": "attention / LayerNorm / projection are PyTorch ops (cuBLAS), the FFN and Postnet convs run on conv_tc_kernel"}
+
     def run_c5():
         gen = make_gen()
         grid = []
@@ -597,6 +627,7 @@ def main():
             extra["lr_large"] = lr_alone(hs_l, ds_l)
             extra["lr_c2"] = lr_alone(hs, ds)
             del hs_l, ds_l
+            extra["c2_with_acoustic_tail"] = run_c2_tail(hs, ds)
             extra["c4"] = run_c4(3)
             extra["c3"] = run_c3(3)
         except Exception as e:  # the headline must survive a failure in the side measurements

@@ -218,6 +218,25 @@ int vtts_dbg_resblock_chain(const float *x, const void *const *w, const void *co
                             int L, int k, const int *dil, int n_units, int has2, float slope, int fp16, int reps,
                             float *ms_out, vtts_stream_t stream);
 
+/* ---- acoustic decoder convolutions (the layer between the LengthRegulator and the generator) -----------------
+ * One Conv1d layer ("same" zero padding, odd kernel, stride 1) on the tcgen05 kernel with CHANNELS-LAST activations, the
+ * layout the transformer blocks already use: replaces nn.Conv1d in PositionwiseFeedForward.w_1 / w_2
+ * (models/tts/fastspeech2/blocks/transformer.py:273-286, called :290-292 between two transposes) and ConvNorm.conv + eval-mode
+ * BatchNorm1d of the Postnet (models/tts/fastspeech2/layers.py:579-612, forward :614-621; the caller folds the BatchNorm
+ * into weight / bias).  weight (cout, cin, k) and bias (cout, or NULL) are fp32 device arrays, packed once per load. */
+typedef struct VttsConv VttsConv;
+int vtts_conv_create(int cin, int cout, int ksize, int dilation, VttsConv **out);
+void vtts_conv_destroy(VttsConv *c);
+/* channels of the 16-bit input operand rows (cin rounded up to the kernel's K chunk: 64, or 32 for cin == 32) */
+int vtts_conv_padded_channels(const VttsConv *c);
+int vtts_conv_load(VttsConv *c, const float *weight, const float *bias, vtts_stream_t stream);
+/* act16: (B, L, padded_channels) 16-bit operand (bf16 / fp16 per `precision`), zero in the padding channels.
+ * value = conv(act) + bias (+ res[b, t, co] when res != NULL, fp32 (B, L, cout));
+ * out_x (B, L, cout) fp32 or NULL receives value; out_a16 (B, L, cout) 16-bit or NULL receives
+ * tanh(value) when act_tanh != 0, else LeakyReLU(value, slope_out) (slope 1 = identity, 0 = ReLU). */
+int vtts_conv_forward(VttsConv *c, const void *act16, int precision, int B, int L, const float *res, float *out_x,
+                      void *out_a16, float slope_out, int act_tanh, vtts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

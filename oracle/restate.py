@@ -335,3 +335,81 @@ def expand_by_path(x: torch.Tensor, duration: torch.Tensor, mask: torch.Tensor) 
     """``torch.matmul(attn.squeeze(1), x.transpose(1, 2)).transpose(1, 2)`` (vits2/generator.py:256-259)."""
     attn = generate_path(duration, mask)
     return torch.matmul(attn.squeeze(1), x.transpose(1, 2)).transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------------
+# Acoustic decoder + Postnet (SURVEY 8f-3)
+#   Decoder / FFTBlock / MultiHeadAttention / PositionwiseFeedForward: models/tts/fastspeech2/blocks/transformer.py:90-298
+#   Postnet: models/tts/fastspeech2/layers.py:571-625 (eval mode: BatchNorm1d uses its running statistics, dropout off)
+# --------------------------------------------------------------------------------------------
+
+
+def sinusoid_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """blocks/utils.py:14-35."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    idx = np.arange(d_hid)[None, :]
+    t = pos / np.power(10000, 2 * (idx // 2) / d_hid)
+    t[:, 0::2] = np.sin(t[:, 0::2])
+    t[:, 1::2] = np.cos(t[:, 1::2])
+    return torch.FloatTensor(t)
+
+
+def fft_decoder_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, mask: torch.Tensor, n_head: int,
+                        prefix: str = "") -> torch.Tensor:
+    """Decoder.forward (transformer.py:132-166, eval, T <= max_seq_len) -> (B, T, d_model).  mask: True on the padding."""
+    B, T, D = x.shape
+    out = x + sd[prefix + "position_enc"][:, :T, :]
+    attn_mask = mask.unsqueeze(1).expand(-1, T, -1)
+    d_k = D // n_head
+    layer = 0
+    while f"{prefix}layer_stack.{layer}.slf_attn.w_qs.weight" in sd:
+        p = f"{prefix}layer_stack.{layer}."
+        # MultiHeadAttention (transformer.py:215-243)
+        res = out
+        q = F.linear(out, sd[p + "slf_attn.w_qs.weight"], sd[p + "slf_attn.w_qs.bias"]).view(B, T, n_head, d_k)
+        k = F.linear(out, sd[p + "slf_attn.w_ks.weight"], sd[p + "slf_attn.w_ks.bias"]).view(B, T, n_head, d_k)
+        v = F.linear(out, sd[p + "slf_attn.w_vs.weight"], sd[p + "slf_attn.w_vs.bias"]).view(B, T, n_head, d_k)
+        q, k, v = (t.permute(2, 0, 1, 3).reshape(-1, T, d_k) for t in (q, k, v))
+        a = torch.bmm(q, k.transpose(1, 2)) / float(np.power(d_k, 0.5))
+        a = a.masked_fill(attn_mask.repeat(n_head, 1, 1), -np.inf)
+        a = torch.softmax(a, dim=2)
+        o = torch.bmm(a, v).view(n_head, B, T, d_k).permute(1, 2, 0, 3).reshape(B, T, -1)
+        o = F.linear(o, sd[p + "slf_attn.fc.weight"], sd[p + "slf_attn.fc.bias"])
+        out = F.layer_norm(o + res, (D,), sd[p + "slf_attn.layer_norm.weight"], sd[p + "slf_attn.layer_norm.bias"])
+        out = out.masked_fill(mask.unsqueeze(-1), 0)
+        # PositionwiseFeedForward (transformer.py:288-298)
+        res = out
+        w1, w2 = sd[p + "pos_ffn.w_1.weight"], sd[p + "pos_ffn.w_2.weight"]
+        h = F.conv1d(out.transpose(1, 2), w1, sd[p + "pos_ffn.w_1.bias"], padding=(w1.shape[-1] - 1) // 2)
+        h = F.conv1d(F.relu(h), w2, sd[p + "pos_ffn.w_2.bias"], padding=(w2.shape[-1] - 1) // 2).transpose(1, 2)
+        out = F.layer_norm(h + res, (D,), sd[p + "pos_ffn.layer_norm.weight"], sd[p + "pos_ffn.layer_norm.bias"])
+        out = out.masked_fill(mask.unsqueeze(-1), 0)
+        layer += 1
+    return out
+
+
+def postnet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = "", eps: float = 1e-5) -> torch.Tensor:
+    """Postnet.forward (layers.py:614-621) in eval mode; x and the result are (B, T, n_mel)."""
+    y = x.transpose(1, 2)
+    n = 0
+    while f"{prefix}convolutions.{n}.0.conv.weight" in sd:
+        n += 1
+    for i in range(n):
+        p = f"{prefix}convolutions.{i}."
+        w = sd[p + "0.conv.weight"]
+        y = F.conv1d(y, w, sd.get(p + "0.conv.bias"), padding=(w.shape[-1] - 1) // 2)
+        y = F.batch_norm(y, sd[p + "1.running_mean"], sd[p + "1.running_var"], sd[p + "1.weight"], sd[p + "1.bias"], False, 0.0, eps)
+        if i < n - 1:
+            y = torch.tanh(y)
+    return y.transpose(1, 2)
+
+
+def acoustic_tail_forward(sd: Dict[str, torch.Tensor], frames: torch.Tensor, mel_len: torch.Tensor, n_head: int) -> torch.Tensor:
+    """FastSpeech2.inference tail (model.py:250-257) with keys ``decoder.*``, ``feats_linear.*``, ``postnet.*`` -> (B, n_mel, T)."""
+    T = frames.shape[1]
+    mask = torch.arange(T)[None, :] >= mel_len[:, None]
+    hs = fft_decoder_forward(sd, frames, mask, n_head, prefix="decoder.")
+    outs = F.linear(hs, sd["feats_linear.weight"], sd["feats_linear.bias"])
+    if "postnet.convolutions.0.0.conv.weight" in sd:
+        outs = postnet_forward(sd, outs, prefix="postnet.") + outs
+    return outs.transpose(1, 2)

@@ -286,6 +286,61 @@ def hifigan_v1_long():
     print("hifigan_v1_long", tuple(y.shape), idx.size)
 
 
+def _randomize_batchnorm(postnet):
+    """Non-trivial running statistics / affine parameters, as a trained Postnet has (deterministic formula, also used by the tests)."""
+    for i, seq in enumerate(postnet.convolutions):
+        bn = seq[1]
+        n = bn.num_features
+        t = torch.arange(n, dtype=torch.float32)
+        bn.running_mean.copy_(0.2 * torch.sin(0.37 * t + i))
+        bn.running_var.copy_(1.0 + 0.5 * torch.cos(0.11 * t + 2 * i))
+        bn.weight.data.copy_(1.0 + 0.3 * torch.sin(0.05 * t + 3 * i))
+        bn.bias.data.copy_(0.1 * torch.cos(0.23 * t + i))
+
+
+def acoustic_tail():
+    """f3: the reference's Decoder (transformer FFT blocks) + feats_linear + Postnet, built stand-alone from the reference's own
+    classes.  `small`: full state dict stored.  `c2`: the C2 width (4 layers, 256 hidden, 1024 filter, Postnet 512) drawn with
+    torch.manual_seed(1234) in a fixed construction order (decoder, feats_linear, postnet) -- the test re-draws the same
+    parameters through the drop-in classes (construction-order parity) and only the checksums + outputs are stored."""
+    ref_loader.load_length_regulator()
+    from models.tts.fastspeech2.blocks.transformer import Decoder  # type: ignore
+    from models.tts.fastspeech2.layers import Postnet  # type: ignore
+
+    out = {}
+    g = torch.Generator().manual_seed(9)
+    for tag, (layers, hidden, filt, emb, B, T) in (("small", (2, 64, 128, 64, 3, 37)), ("c2", (4, 256, 1024, 512, 2, 50))):
+        cfg = {"decoder_head": 2, "conv_filter_size": filt, "conv_kernel_size": [9, 1], "decoder_dropout": 0.2}
+        torch.manual_seed(1234)
+        dec = Decoder(layers, hidden, 1000, cfg).eval()
+        lin = torch.nn.Linear(hidden, 80).eval()
+        post = Postnet(80, {"embedding_dim": emb, "conv_layers": 5, "kernel_size": 5}).eval()
+        with torch.no_grad():
+            _randomize_batchnorm(post)
+        frames = torch.randn(B, T, hidden, generator=g)
+        mel_len = torch.tensor([T, T - 9, 5][:B])
+        mask = torch.arange(T)[None] >= mel_len[:, None]
+        frames = frames.masked_fill(mask.unsqueeze(-1), 0.0)      # the regulator pads with zeros
+        with torch.no_grad():
+            hs, _ = dec(frames, mask)
+            outs = lin(hs)
+            mel = (post(outs) + outs).transpose(1, 2)
+            pn = post(outs)
+        out.update({f"{tag}.frames": frames.numpy(), f"{tag}.mel_len": mel_len.numpy(), f"{tag}.dec": hs.numpy(),
+                    f"{tag}.postnet": pn.numpy(), f"{tag}.mel": mel.contiguous().numpy()})
+        sd = {}
+        sd.update({"decoder." + k: v for k, v in dec.state_dict().items()})
+        sd.update({"feats_linear." + k: v for k, v in lin.state_dict().items()})
+        sd.update({"postnet." + k: v for k, v in post.state_dict().items()})
+        keys = sorted(sd)
+        out[f"{tag}.keys"] = np.array(keys)
+        out[f"{tag}.sums"] = np.array([float(sd[k].double().sum()) for k in keys])
+        if tag == "small":
+            out.update(sd_to_np({k: v for k, v in sd.items() if k != "decoder.position_enc"}, prefix="small.sd."))
+        print("acoustic_tail", tag, tuple(mel.shape), len(keys))
+    np.savez_compressed(os.path.join(OUT, "acoustic_tail.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs /root/reference"
     only = sys.argv[1:]
@@ -301,6 +356,7 @@ if __name__ == "__main__":
     vits2_small()
     fastspeech2_capture()
     hifigan_v1_long()
+    acoustic_tail()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -124,6 +124,7 @@ struct TcConvParams {
     int trace;                 // debug: block 0 records per-tile clock64() stamps into g_trace
     int stream_hint;           // 1: activation / residual reads carry the L2 evict-first policy
     int x_cl;                  // out_x is channels-last fp32 [b][t][c] (input of the chain kernel) instead of time-packed
+    int act_tanh;              // the 16-bit copy is tanh(value) instead of LeakyReLU(value) (Postnet, layers.py:615-617)
     int reverse;               // walk the tiles last-to-first (alternates per launch: the tail the previous kernel just
                                // wrote is still in L2 when this kernel starts reading there)
     // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
@@ -221,7 +222,8 @@ __device__ __forceinline__ void epi_group16_edge(const uint32_t (&v)[16], float 
             if (p.accumulate) val = p.out_x[xo] + val;
             if (p.divide_by > 0.f) val = val * p.inv_div;
             if (p.out_x) p.out_x[xo] = val;
-            if (p.out_a) p.out_a[((long long)b * p.L_out + t) * p.out_a_ld + co] = cvt16(lrelu_max(val, p.slope_out), FMT);
+            if (p.out_a)
+                p.out_a[((long long)b * p.L_out + t) * p.out_a_ld + co] = cvt16(p.act_tanh ? tanhf(val) : lrelu_max(val, p.slope_out), FMT);
         }
     }
 }
@@ -553,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                        : (R && C && !D && X && !A) ? EPI_RCX
                        : (R && C && D && X && A) ? EPI_RCDXA
                        : (R && C && D && X && !A) ? EPI_RCDX : EPI_GENERIC;
-        const bool unit = p.out_stride == 1 && p.out_off0 == 0 && p.n_total == p.cout && mode != EPI_GENERIC && !p.x_cl;
+        const bool unit = p.out_stride == 1 && p.out_off0 == 0 && p.n_total == p.cout && mode != EPI_GENERIC && !p.x_cl && !p.act_tanh;
         const int c_ct = (!A || p.out_a_ld == p.cout) ? p.cout : 0;
         // polyphase upsample: fp32 x + 16-bit copy, nothing read; 32-bit index math is safe below 2^31 elements per row
         const bool poly = !R && !C && !D && X && (A || p.x_cl) && p.out_stride > 1 && (long long)p.L4 * p.cout * 4 < 0x7fffffffLL &&
@@ -2775,4 +2777,83 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
     cudaFree(a); cudaFree(wp); cudaFree(oa); cudaFree(ox); cudaFree(rcl);
     if (!rc && e != cudaSuccess) return set_error(VTTS_E_CUDA, "vtts_dbg_conv1d_tc: %s", cudaGetErrorString(e));
     return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone Conv1d layer on the tcgen05 kernel (channels-last activations): the convolutions of the acoustic decoder
+// between the LengthRegulator and the generator -- PositionwiseFeedForward w_1 / w_2 (blocks/transformer.py:265-298) and
+// the Postnet's five Conv1d + eval-mode BatchNorm (fastspeech2/layers.py:571-625, BatchNorm folded by the caller).
+// ---------------------------------------------------------------------------------------------
+struct VttsConv {
+    int cin = 0, cout = 0, k = 0, dil = 1, ci_pad = 0, n_pad = 0;
+    uint16_t *w16[2] = {nullptr, nullptr};
+    float *bias = nullptr;
+    bool loaded = false;
+};
+
+extern "C" int vtts_conv_create(int cin, int cout, int ksize, int dilation, VttsConv **out) {
+    VTTS_REQUIRE(out, "vtts_conv_create: null pointer");
+    VTTS_REQUIRE(cin >= 1 && cout >= 1 && ksize >= 1 && ksize % 2 == 1 && dilation >= 1, "vtts_conv_create: bad shape");
+    if ((ksize - 1) * dilation > HALO_MAX) return set_error(VTTS_E_UNSUPPORTED, "vtts_conv_create: (kernel-1)*dilation > %d", HALO_MAX);
+    VttsConv *c = new (std::nothrow) VttsConv();
+    if (!c) return set_error(VTTS_E_INVALID, "vtts_conv_create: out of host memory");
+    c->cin = cin; c->cout = cout; c->k = ksize; c->dil = dilation;
+    c->ci_pad = ci_pad_of(cin); c->n_pad = pad_to(cout, TM);
+    *out = c;
+    return VTTS_OK;
+}
+
+extern "C" void vtts_conv_destroy(VttsConv *c) {
+    if (!c) return;
+    cudaFree(c->w16[0]); cudaFree(c->w16[1]); cudaFree(c->bias);
+    delete c;
+}
+
+extern "C" int vtts_conv_padded_channels(const VttsConv *c) {
+    VTTS_REQUIRE(c, "vtts_conv_padded_channels: null handle");
+    return c->ci_pad;
+}
+
+extern "C" int vtts_conv_load(VttsConv *c, const float *weight, const float *bias, vtts_stream_t stream) {
+    VTTS_REQUIRE(c && weight, "vtts_conv_load: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)c->k * c->n_pad * c->ci_pad;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 8192) blocks = 8192;
+    for (int fmt = 0; fmt < 2; ++fmt) {
+        if (!c->w16[fmt]) VTTS_CHECK_CUDA(cudaMalloc(&c->w16[fmt], n * sizeof(uint16_t)));
+        pack_tc_kernel<<<blocks, 256, 0, st>>>(weight, c->w16[fmt], fmt, 0, c->cin, c->cout, c->k, 1, c->k, c->n_pad, c->ci_pad, c->cout);
+        VTTS_CHECK_LAUNCH();
+    }
+    if (bias) {
+        if (!c->bias) VTTS_CHECK_CUDA(cudaMalloc(&c->bias, (size_t)c->cout * sizeof(float)));
+        VTTS_CHECK_CUDA(cudaMemcpyAsync(c->bias, bias, (size_t)c->cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (c->bias) {
+        cudaFree(c->bias);
+        c->bias = nullptr;
+    }
+    c->loaded = true;
+    return VTTS_OK;
+}
+
+extern "C" int vtts_conv_forward(VttsConv *c, const void *act16, int precision, int B, int L, const float *res, float *out_x,
+                                 void *out_a16, float slope_out, int act_tanh, vtts_stream_t stream) {
+    VTTS_REQUIRE(c && act16 && (out_x || out_a16), "vtts_conv_forward: null pointer");
+    VTTS_REQUIRE(c->loaded, "vtts_conv_forward: no weights loaded");
+    VTTS_REQUIRE(B >= 1 && L >= 1, "vtts_conv_forward: B and L must be >= 1");
+    if (out_a16 && c->cout % 32 != 0) return set_error(VTTS_E_UNSUPPORTED, "vtts_conv_forward: 16-bit output needs cout %% 32 == 0 (cout = %d)", c->cout);
+    if (precision != VTTS_PRECISION_BF16 && precision != VTTS_PRECISION_FP16)
+        return set_error(VTTS_E_INVALID, "vtts_conv_forward: precision must be bf16 or fp16");
+    const int fmt = precision == VTTS_PRECISION_BF16 ? VTTS_FMT_BF16 : VTTS_FMT_FP16;
+    TcConvParams p{};
+    p.bias = c->bias; p.res = res; p.out_x = out_x; p.out_a = (uint16_t *)out_a16; p.out_a_ld = c->cout;
+    p.slope_out = slope_out; p.act_tanh = act_tanh; p.x_cl = 1;
+    p.n_total = c->cout; p.cout = c->cout; p.L_out = L; p.n_pos = L; p.out_stride = 1; p.out_off0 = 0;
+    p.taps = c->k; p.tap_off0 = -(c->k - 1) / 2 * c->dil; p.tap_step = c->dil;
+    TcLaunch Lc;
+    int rc = tc_prepare(Lc, fmt, (const uint16_t *)act16, B, L, c->ci_pad, c->w16[fmt], c->n_pad, p);
+    if (rc) return rc;
+    Lc.pdl = false;
+    return tc_launch(Lc, (cudaStream_t)stream);
 }

@@ -6,6 +6,7 @@ the C ABI in include/vtts_b200.h); this package is plumbing: parameter container
 reference's ``state_dict`` keys, ctypes calls, batch sharding across ranks.
 """
 from . import _lib
+from .acoustic import AcousticTail, ConvNorm, Decoder, FFTBlock, MultiHeadAttention, PositionwiseFeedForward, Postnet
 from .dropin import install, uninstall
 from .gaussian_upsampling import GaussianUpsampling
 from .hifigan import GraphedForward, HiFiGAN, ResidualBlock
@@ -18,6 +19,6 @@ from .vits2_path import expand_by_path, generate_path
 __all__ = [
     "HiFiGAN", "ResidualBlock", "GraphedForward", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
     "Synthesizer", "PendingSynthesis", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall", "generate_path",
-    "expand_by_path",
+    "expand_by_path", "Decoder", "FFTBlock", "MultiHeadAttention", "PositionwiseFeedForward", "Postnet", "ConvNorm", "AcousticTail",
 ]
 __version__ = "0.1.0"

@@ -60,6 +60,12 @@ SIGNATURES = {
     "vtts_gen_set_valid_lengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vtts_gen_last_launch_count": (C.c_int, [C.c_void_p]),
     "vtts_gen_set_range_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vtts_conv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vtts_conv_destroy": (None, [C.c_void_p]),
+    "vtts_conv_padded_channels": (C.c_int, [C.c_void_p]),
+    "vtts_conv_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtts_conv_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_int, C.c_void_p]),
     "vtts_dbg_conv1d_fp32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "vtts_dbg_conv1d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

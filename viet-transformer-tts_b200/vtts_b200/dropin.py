@@ -9,7 +9,8 @@
 Replaced symbols (reference file:line):
   models/gan_tts/hifigan/generator.py:16   HiFiGAN
   models/gan_tts/hifigan/layers.py:16      ResidualBlock
-  models/tts/fastspeech2/layers.py:410     LengthRegulator      :465 GaussianUpsampling
+  models/tts/fastspeech2/layers.py:410     LengthRegulator      :465 GaussianUpsampling      :571 Postnet
+  models/tts/fastspeech2/blocks/transformer.py:265   PositionwiseFeedForward (FFT-block convs of encoder and decoder)
   models/gan_tts/vits2/layers.py:107       Generator
   models/gan_tts/vits2/sublayers.py:215    ResBlock1      :312 ResBlock2
   models/gan_tts/vits2/utils.py:111        generate_path (also the name imported into vits2/generator.py:8)
@@ -25,7 +26,8 @@ from typing import Dict, Tuple
 _TARGETS = {
     "models.gan_tts.hifigan.generator": ("HiFiGAN",),
     "models.gan_tts.hifigan.layers": ("ResidualBlock",),
-    "models.tts.fastspeech2.layers": ("LengthRegulator", "GaussianUpsampling"),
+    "models.tts.fastspeech2.layers": ("LengthRegulator", "GaussianUpsampling", "Postnet"),
+    "models.tts.fastspeech2.blocks.transformer": ("PositionwiseFeedForward",),
     "models.gan_tts.jets.alignments": ("GaussianUpsampling",),
     "models.gan_tts.vits2.layers": ("Generator",),
     "models.gan_tts.vits2.sublayers": ("ResBlock1", "ResBlock2"),
@@ -35,12 +37,13 @@ _saved: Dict[Tuple[str, str], object] = {}
 
 
 def _replacements():
-    from . import gaussian_upsampling, hifigan, length_regulator, vits2, vits2_path
+    from . import acoustic, gaussian_upsampling, hifigan, length_regulator, vits2, vits2_path
 
     return {
         "HiFiGAN": hifigan.HiFiGAN, "ResidualBlock": hifigan.ResidualBlock,
         "LengthRegulator": length_regulator.LengthRegulator, "Generator": vits2.Generator,
         "GaussianUpsampling": gaussian_upsampling.GaussianUpsampling,
+        "Postnet": acoustic.Postnet, "PositionwiseFeedForward": acoustic.PositionwiseFeedForward,
         "ResBlock1": vits2.ResBlock1, "ResBlock2": vits2.ResBlock2, "generate_path": vits2_path.generate_path,
     }
 

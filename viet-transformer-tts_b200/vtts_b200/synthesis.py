@@ -45,11 +45,16 @@ class PendingSynthesis:
 class Synthesizer:
     def __init__(self, generator, length_regulator: Optional[LengthRegulator] = None,
                  frames_to_mel: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                 device: Optional[torch.device] = None, trim_padding: bool = True):
+                 device: Optional[torch.device] = None, trim_padding: bool = True,
+                 acoustic_tail: Optional[Callable[[torch.Tensor, torch.Tensor], torch.Tensor]] = None):
+        """``acoustic_tail(frames (B,T,D), mel_len (B,)) -> mel (B, n_mel, T)`` (e.g. :class:`vtts_b200.AcousticTail`:
+        decoder + Postnet on the conv kernels) takes precedence over ``frames_to_mel(frames)``; without either the
+        first ``in_channels`` features stand in for the decoder."""
         self.generator = generator
         self.length_regulator = length_regulator or LengthRegulator()
         cfg = generator._gen_config()
         self.frames_to_mel = frames_to_mel or slice_decoder_stand_in(cfg.in_channels)
+        self.acoustic_tail = acoustic_tail
         self.device = torch.device(device) if device is not None else next(generator.parameters()).device
         self._pinned_out = None
         self._copy_stream = None            # submit(): device->host copies run here, behind the next batch's kernels
@@ -63,7 +68,11 @@ class Synthesizer:
     @torch.no_grad()
     def __call__(self, hs: torch.Tensor, ds: torch.Tensor, alpha: float = 1.0, to_host: bool = True
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """hs (B,Tmax,D) float, ds (B,Tmax) int64 -- host (ideally pinned) or device tensors."""
+        """hs (B,Tmax,D) float, ds (B,Tmax) int64 -- host (ideally pinned) or device tensors.
+
+        With ``to_host`` (default) the returned waveform is a VIEW of one pinned host buffer that this object reuses:
+        the next ``__call__`` overwrites it.  Consume it (write the file, ``.clone()``) before calling again, or use
+        ``to_host=False`` for a device tensor you own; ``submit()`` rotates two buffers (see ``PendingSynthesis.result``)."""
         dev = self.device
         # Durations that arrive on the host are summed on the host (a few hundred integers): the output length is then
         # known without the LengthRegulator's device->host read, and the whole call is queued without a sync.
@@ -76,7 +85,7 @@ class Synthesizer:
         hs_d = hs.to(dev, non_blocking=True)
         ds_d = ds.to(dev, non_blocking=True)
         frames, mel_len = self.length_regulator.forward_with_lengths(hs_d, ds_d, alpha, max_len=max_len)
-        mel = self.frames_to_mel(frames)
+        mel = self.acoustic_tail(frames, mel_len) if self.acoustic_tail is not None else self.frames_to_mel(frames)
         if self.trim_padding and hasattr(self.generator, "forward_trimmed"):
             wav = self.generator.forward_trimmed(mel, mel_len)
         else:
