@@ -1,7 +1,7 @@
 """Turn gpurun_out/ artefacts of tools/gpu_full.sh into the tracked summaries under profiles/."""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles"); G = os.path.join(ROOT, "gpurun_out")
+OUT = os.environ.get("VTTS_PROFILE_OUT", os.path.join(ROOT, "profiles")); G = os.path.join(ROOT, "gpurun_out")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 os.makedirs(OUT, exist_ok=True)
 
@@ -29,9 +29,10 @@ traffic = sum(r[5] + r[6] for r in rows)
 agg = {}
 for r in rows:
     a = agg.setdefault(r[1], [0, 0.0, 0.0]); a[0] += 1; a[1] += r[4]; a[2] += r[5] + r[6]
+n_l = len(rows)
 md = [f"# {tag}: launch list of one HiFi-GAN V1 forward (fp16, B=16, T=759, no padding trim), ncu\n",
       "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-      "-k 'regex:conv_tc|unit_tc|unit64_tc|conv_post|cf_to_cl' -s 52 -c 52 --csv python tools/ncu_forward.py`",
+      f"-k 'regex:conv_tc|unit_tc|unit64_tc|chain_tc|conv_post|cf_to_cl' -s {n_l} -c {n_l} --csv python tools/ncu_forward.py`",
       "(per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes)\n",
       "| kernel | launches | total us | share | DRAM read+write MB |", "|---|---|---|---|---|"]
 for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -47,11 +48,26 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum", "sm__cycles_elapsed.max",
-        "sm__inst_executed_pipe_tensor.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-for rep, what in (("prof_unit_c128_k11", "stage 1 (128 ch) fused unit k=11, d=1 (`unit_tc_kernel`) -- tensor / L2-weight-stream bound"),
-                  ("prof_unit64_c64_k11", "stage 2 (64 ch) fused unit k=11, d=1 (`unit64_tc_kernel`, M=64, resident weights)"),
-                  ("prof_unit64_c32_k3", "stage 3 (32 ch) fused unit k=3, d=1 (`unit64_tc_kernel`) -- HBM-bound"),
-                  ("prof_conv_c256_k11", "stage 0 (256 ch) k=11: conv1 then conv2 (`conv_tc_kernel`)")):
+        "sm__inst_executed_pipe_tensor.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
+REPORTS = {
+    "r01": (("prof_unit_c128_k11", "stage 1 (128 ch) fused unit k=11, d=1 (`unit_tc_kernel`) -- tensor / L2-weight-stream bound"),
+            ("prof_unit64_c64_k11", "stage 2 (64 ch) fused unit k=11, d=1 (`unit64_tc_kernel`, M=64, resident weights)"),
+            ("prof_unit64_c32_k3", "stage 3 (32 ch) fused unit k=3, d=1 (`unit64_tc_kernel`) -- HBM-bound"),
+            ("prof_conv_c256_k11", "stage 0 (256 ch) k=11: conv1 then conv2 (`conv_tc_kernel`)")),
+    "r02": (("prof_chain_c32_k11", "stage 3 (32 ch) ResidualBlock k=11, all 6 convs in one launch (`chain_tc_kernel<32>`, streamed weights)"),
+            ("prof_chain_c32_k3", "stage 3 (32 ch) ResidualBlock k=3 (`chain_tc_kernel<32>`, resident weights)"),
+            ("prof_chain_c64_k7", "stage 2 (64 ch) ResidualBlock k=7 (`chain_tc_kernel<64>`, streamed weights)"),
+            ("prof_unit_c128_k11", "stage 1 (128 ch) fused unit k=11, d=1 (`unit_tc_kernel`)"),
+            ("prof_conv_c256_k11", "stage 0 (256 ch) k=11: conv1 then conv2 (`conv_tc_kernel`)"),
+            ("prof_up1_256_128", "upsample 256 -> 128, x8 polyphase (`conv_tc_kernel`, fp32 time-packed + 16-bit copy out)"),
+            ("prof_up3_64_32", "upsample 64 -> 32, x2 polyphase (`conv_tc_kernel`, fp32 channels-last out for the chain kernel)"),
+            ("prof_conv_post", "output conv 32 -> 1, k=7 + tanh on the channels-last stream (`conv_post_cl_kernel`)"),
+            ("prof_lr_gather", "LengthRegulator gather at (256, 330 -> ~2200, 256) (`lr_gather_kernel`) -- HBM-bound"),
+            ("prof_gauss", "GaussianUpsampling (16, 120 -> ~760, 256) (`gauss_upsample_kernel`)"),
+            ("prof_path", "vits2 generate_path / expansion (16, 192, 120 -> ~760) (`path_generate_kernel`, `path_expand_kernel`)")),
+}
+for rep, what in REPORTS.get(tag, REPORTS["r02"]):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -60,7 +76,7 @@ for rep, what in (("prof_unit_c128_k11", "stage 1 (128 ch) fused unit k=11, d=1 
     hdr, units = rr[0], rr[1]
     idx = {h: i for i, h in enumerate(hdr)}
     md.append(f"## ncu --set full: {what}\n")
-    md.append(f"Report: `{rep}.ncu-rep` (scratch, not committed); command in `tools/gpu_full.sh`\n")
+    md.append(f"Report: `{rep}.ncu-rep` (scratch, not committed); command in `tools/gpu_full.sh` (r01) / `tools/gpu_profile_r02.sh` (r02)\n")
     nl = len(rr) - 2
     md.append("| metric | unit | " + " | ".join(f"launch {i + 1}" for i in range(nl)) + " |"); md.append("|---|---|" + "---|" * nl)
     for w in want:

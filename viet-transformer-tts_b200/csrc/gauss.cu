@@ -7,7 +7,10 @@
 // One fused kernel: a CTA owns FR consecutive output frames of one batch row, builds the token centres with
 // a block prefix sum in shared memory, each warp runs the softmax of FRW frames at once (probabilities kept
 // in shared memory) and accumulates the weighted sum of token rows with every hs row read once per FRW
-// frames (coalesced, 128 bytes per warp access).  Floating point: parity within 1e-5 of the fp32 oracle.
+// frames (coalesced, 128 bytes per warp access), only over the tokens whose probability is non-zero for one of those
+// frames.  Floating point: parity within 1e-5 of the fp32 oracle.
+// Work per call: B * T_feats * (window ~ 64 frames / mean duration) * D FMA; bytes: hs rows of the window re-read per 4
+// frames (L1/L2 hits), out B * T_feats * D * 4 written once.
 #include "common.cuh"
 
 namespace vtts {
@@ -96,9 +99,25 @@ gauss_upsample_kernel(const float *__restrict__ hs, const long long *__restrict_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum[f] += __shfl_xor_sync(0xffffffffu, sum[f], o);
     __syncwarp();
-    for (int j = lane; j < T_text; j += 32)
+    // normalise; remember the token window outside of which every probability of these frames is exactly 0 (exp
+    // underflows to 0 beyond |t - c_j| of about 32 frames at delta = 0.1): the weighted sum below skips those tokens,
+    // which adds exact zeros in the reference's matmul - bit-identical for finite hs
+    int jlo = T_text, jhi = 0;
+    for (int j = lane; j < T_text; j += 32) {
+        bool nz = false;
 #pragma unroll
-        for (int f = 0; f < GU_FRW; ++f) p[f * T_text + j] = __fdiv_rn(p[f * T_text + j], sum[f]);
+        for (int f = 0; f < GU_FRW; ++f) {
+            const float v = __fdiv_rn(p[f * T_text + j], sum[f]);
+            p[f * T_text + j] = v;
+            nz |= (v != 0.f);                          // (NaN rows - everything masked - stay in the window)
+        }
+        if (nz) { jlo = min(jlo, j); jhi = max(jhi, j + 1); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+        jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+    }
     __syncwarp();
 
     // weighted sum: every hs row is read once per GU_FRW frames (layers.py:517)
@@ -109,7 +128,7 @@ gauss_upsample_kernel(const float *__restrict__ hs, const long long *__restrict_
         for (int f = 0; f < GU_FRW; ++f)
 #pragma unroll
             for (int q = 0; q < GU_DCH; ++q) acc[f][q] = 0.f;
-        for (int j = 0; j < T_text; ++j) {
+        for (int j = jlo; j < jhi; ++j) {
             float pj[GU_FRW];
 #pragma unroll
             for (int f = 0; f < GU_FRW; ++f) pj[f] = p[f * T_text + j];

@@ -14,7 +14,7 @@ namespace vtts {
 
 constexpr int LR_THREADS = 256;
 constexpr int LR_WARPS = LR_THREADS / 32;
-constexpr int LR_FRAMES_PER_CTA = 32;
+constexpr int LR_FRAMES_PER_CTA = 64;
 
 __device__ __forceinline__ long long warp_inclusive_scan(long long v, int lane) {
 #pragma unroll
@@ -137,29 +137,49 @@ lr_gather_kernel(const unsigned char *__restrict__ xs, const long long *__restri
     const unsigned char *xrow = xs + (long long)b * Tmax * row_bytes;
     unsigned char *orow = out + (long long)b * T_out * row_bytes;
 
-    for (int f = warp; f < LR_FRAMES_PER_CTA; f += LR_WARPS) {
-        const long long t = t0 + f;
-        if (t >= T_out) break;
-        V *dst = reinterpret_cast<V *>(orow + t * row_bytes);
-        if (t < len) {
-            // j = #{i : cum[i] <= t}  (upper bound); warp-uniform binary search in smem
-            int lo = 0, hi = Tmax;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (cum[mid] <= t) lo = mid + 1; else hi = mid;
-            }
-            const V *src = reinterpret_cast<const V *>(xrow + (long long)lo * row_bytes);
-            long long i = lane;
-            // 4 independent 128-bit requests in flight per lane
-            for (; i + 96 < nvec; i += 128) {
-                V a = __ldg(src + i), c = __ldg(src + i + 32), d = __ldg(src + i + 64),
-                  e = __ldg(src + i + 96);
-                dst[i] = a; dst[i + 32] = c; dst[i + 64] = d; dst[i + 96] = e;
-            }
-            for (; i < nvec; i += 32) dst[i] = __ldg(src + i);
-        } else {
-            for (long long i = lane; i < nvec; i += 32) dst[i] = pad;
+    // Each warp owns LR_FRAMES_PER_CTA / LR_WARPS CONSECUTIVE frames and walks the tokens that cover them: a token row is
+    // loaded once (one 512-byte chunk per pass, kept in registers) and stored once per frame it expands to - the reads
+    // drop by the mean duration, and the kernel is bound by its streaming stores.
+    constexpr int FPW = LR_FRAMES_PER_CTA / LR_WARPS;
+    const long long ta = t0 + (long long)warp * FPW;
+    long long tb = ta + FPW;
+    if (tb > T_out) tb = T_out;
+    if (ta >= tb) return;
+    const long long live_end = tb < len ? tb : len;              // frames [ta, live_end) are copies, [live_end, tb) padding
+    if (ta < live_end) {
+        // j = #{i : cum[i] <= ta}  (upper bound); warp-uniform binary search in smem
+        int lo = 0, hi = Tmax;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (cum[mid] <= ta) lo = mid + 1; else hi = mid;
         }
+        long long t = ta;
+        for (int j = lo; t < live_end; ++j) {
+            long long te = cum[j];                                // frames [t, te) repeat token j (te == t: duration 0)
+            if (te > live_end) te = live_end;
+            if (te <= t) continue;
+            const V *src = reinterpret_cast<const V *>(xrow + (long long)j * row_bytes);
+            for (long long i0 = 0; i0 < nvec; i0 += 128) {        // 4 independent 128-bit requests in flight per lane
+                const long long i = i0 + lane;
+                V a = pad, c = pad, d = pad, e = pad;
+                if (i < nvec) a = __ldg(src + i);
+                if (i + 32 < nvec) c = __ldg(src + i + 32);
+                if (i + 64 < nvec) d = __ldg(src + i + 64);
+                if (i + 96 < nvec) e = __ldg(src + i + 96);
+                for (long long tt = t; tt < te; ++tt) {
+                    V *dst = reinterpret_cast<V *>(orow + tt * row_bytes);
+                    if (i < nvec) __stcs(dst + i, a);
+                    if (i + 32 < nvec) __stcs(dst + i + 32, c);
+                    if (i + 64 < nvec) __stcs(dst + i + 64, d);
+                    if (i + 96 < nvec) __stcs(dst + i + 96, e);
+                }
+            }
+            t = te;
+        }
+    }
+    for (long long t = (ta > live_end ? ta : live_end); t < tb; ++t) {
+        V *dst = reinterpret_cast<V *>(orow + t * row_bytes);
+        for (long long i = lane; i < nvec; i += 32) __stcs(dst + i, pad);
     }
 }
 
