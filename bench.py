@@ -460,11 +460,13 @@ def main():
                "tflops": float(ds.sum()) * FLOP_PER_FRAME_V1_IN384 * steps / (worst * 1e-3) / 1e12 / world}
         if world > 1 and args.gather:
             wav_len = r["mel_len"] * gen3.upsample_factor
+            vtts_b200.gather_waveforms(r["wav"], wav_len, idx, 64)      # warm-up: NCCL channel set-up
             barrier()
             t0 = time.perf_counter()
             vtts_b200.gather_waveforms(r["wav"], wav_len, idx, 64)
             barrier()
             out["gather_ms"] = 1e3 * (time.perf_counter() - t0)
+            out["gather_bytes_per_rank"] = int(r["wav"].numel()) * 4
             out["gather_note"] = "optional final exchange: four all_gather calls over NCCL, padded to the global maximum"
         del gen3
         return out
