@@ -167,11 +167,27 @@ class MultiHeadAttention(nn.Module):
         self.fc = nn.Linear(n_head * d_v, d_model)
         self.dropout = nn.Dropout(dropout)
 
-    def forward(self, q, k, v, mask=None):
+    def forward(self, q, k, v, mask=None, need_weights: bool = True):
         d_k, d_v, n_head = self.d_k, self.d_v, self.n_head
         sz_b, len_q, _ = q.size()
         len_k, len_v = k.size(1), v.size(1)
         residual = q
+        if (not need_weights and q is k and k is v and q.is_cuda and mask is not None
+                and not (torch.is_grad_enabled() and (q.requires_grad or self.w_qs.weight.requires_grad))):
+            # synthesis path of the drop-in Decoder: one projection GEMM for q, k, v and one fused attention kernel
+            # (same arithmetic in fp32: softmax(q k^T / sqrt(d_k) with -inf on the masked keys) v; the attention matrix
+            # itself is not materialised, so callers that want it use need_weights=True)
+            w = torch.cat([self.w_qs.weight, self.w_ks.weight, self.w_vs.weight], 0)
+            b = torch.cat([self.w_qs.bias, self.w_ks.bias, self.w_vs.bias], 0)
+            qkv = F.linear(q, w, b)
+            qh = qkv[..., : n_head * d_k].view(sz_b, len_q, n_head, d_k).transpose(1, 2)
+            kh = qkv[..., n_head * d_k: 2 * n_head * d_k].view(sz_b, len_k, n_head, d_k).transpose(1, 2)
+            vh = qkv[..., 2 * n_head * d_k:].view(sz_b, len_v, n_head, d_v).transpose(1, 2)
+            keep = ~mask[:, :1, :].unsqueeze(1)                       # (B, 1, 1, len_k): the mask rows are identical (key padding)
+            output = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=keep)
+            output = output.transpose(1, 2).reshape(sz_b, len_q, n_head * d_v)
+            output = self.dropout(self.fc(output))
+            return self.layer_norm(output + residual), None
         q = self.w_qs(q).view(sz_b, len_q, n_head, d_k).permute(2, 0, 1, 3).contiguous().view(-1, len_q, d_k)
         k = self.w_ks(k).view(sz_b, len_k, n_head, d_k).permute(2, 0, 1, 3).contiguous().view(-1, len_k, d_k)
         v = self.w_vs(v).view(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).contiguous().view(-1, len_v, d_v)
@@ -226,8 +242,8 @@ class FFTBlock(nn.Module):
         self.slf_attn = MultiHeadAttention(n_head, d_model, d_k, d_v, dropout=dropout)
         self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, kernel_size, dropout=dropout)
 
-    def forward(self, enc_input, mask=None, slf_attn_mask=None):
-        enc_output, enc_slf_attn = self.slf_attn(enc_input, enc_input, enc_input, mask=slf_attn_mask)
+    def forward(self, enc_input, mask=None, slf_attn_mask=None, need_weights: bool = True):
+        enc_output, enc_slf_attn = self.slf_attn(enc_input, enc_input, enc_input, mask=slf_attn_mask, need_weights=need_weights)
         if mask is not None:
             enc_output = enc_output.masked_fill(mask.unsqueeze(-1), 0)
         enc_output = self.pos_ffn(enc_output)
@@ -264,7 +280,7 @@ class Decoder(nn.Module):
             mask = mask[:, :max_len]
             slf_attn_mask = slf_attn_mask[:, :, :max_len]
         for dec_layer in self.layer_stack:
-            dec_output, _ = dec_layer(dec_output, mask=mask, slf_attn_mask=slf_attn_mask)
+            dec_output, _ = dec_layer(dec_output, mask=mask, slf_attn_mask=slf_attn_mask, need_weights=return_attns)
         return dec_output, mask
 
 
