@@ -166,6 +166,7 @@ class MultiHeadAttention(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model)
         self.fc = nn.Linear(n_head * d_v, d_model)
         self.dropout = nn.Dropout(dropout)
+        self.precision = DEFAULT_PRECISION      # operand format of the fused synthesis-path attention ("fp32": exact)
 
     def forward(self, q, k, v, mask=None, need_weights: bool = True):
         d_k, d_v, n_head = self.d_k, self.d_v, self.n_head
@@ -184,7 +185,13 @@ class MultiHeadAttention(nn.Module):
             kh = qkv[..., n_head * d_k: 2 * n_head * d_k].view(sz_b, len_k, n_head, d_k).transpose(1, 2)
             vh = qkv[..., 2 * n_head * d_k:].view(sz_b, len_v, n_head, d_v).transpose(1, 2)
             keep = ~mask[:, :1, :].unsqueeze(1)                       # (B, 1, 1, len_k): the mask rows are identical (key padding)
-            output = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=keep)
+            if self.precision != "fp32":
+                # 16-bit operands, fp32 softmax / accumulation inside the fused kernel (tensor cores): the same operand
+                # rounding the conv kernels apply; fp32 SDPA runs on the CUDA cores and took 0.49 ms per block at C2
+                dt = torch.float16 if self.precision == "fp16" else torch.bfloat16
+                output = F.scaled_dot_product_attention(qh.to(dt), kh.to(dt), vh.to(dt), attn_mask=keep).float()
+            else:
+                output = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=keep)
             output = output.transpose(1, 2).reshape(sz_b, len_q, n_head * d_v)
             output = self.dropout(self.fc(output))
             return self.layer_norm(output + residual), None
