@@ -368,3 +368,56 @@ def test_padding_trim_with_more_rows_than_the_limit_table():
     for b in (0, 1, 128, 255, 256, 259):
         n = int(lens[b]) * 256
         assert torch.equal(full[b, :, :n], trimmed[b, :, :n])
+
+
+def test_padding_trim_on_a_config_with_a_longer_lookahead_than_v1():
+    """Advisor finding: the per-layer trim margins must follow the configuration (scales [4,4,4,4] need about 22 frames of
+    look-ahead at stage 0 - more than V1's 12); the caller's margin is only a lower bound, never a cap."""
+    torch.manual_seed(11)
+    m = vtts_b200.HiFiGAN(upsample_scales=[4, 4, 4, 4], upsample_kernel_sizes=[8, 8, 8, 8]).to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    B, T = 5, 90
+    c = torch.randn(B, 80, T, generator=g).to(DEV)
+    lens = torch.tensor([90, 61, 33, 7, 1])
+    with torch.no_grad():
+        full = m(c)
+        m.forward_trimmed(c * 30.0, torch.full((B,), T, device=DEV))         # poison the workspace beyond the valid parts
+        for margin in (None, 0, 3):
+            trimmed = m.forward_trimmed(c, lens.to(DEV), margin_frames=margin)
+            for b in range(B):
+                n = int(lens[b]) * m.upsample_factor
+                assert torch.equal(full[b, :, :n], trimmed[b, :, :n]), (margin, b)
+
+
+def test_vits2_generator_trim_through_the_synthesizer_entry():
+    torch.manual_seed(5)
+    m = vtts_b200.Generator(192, resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                            upsample_rates=[8, 8, 2, 2], upsample_initial_channel=512, upsample_kernel_sizes=[16, 16, 4, 4]).to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 192, 40, generator=g).to(DEV)
+    lens = torch.tensor([40, 23, 9], device=DEV)
+    with torch.no_grad():
+        full = m(x)
+        trimmed = m.forward_trimmed(x, lens)
+    for b in range(3):
+        n = int(lens[b]) * 256
+        assert torch.equal(full[b, :, :n], trimmed[b, :, :n]), b
+
+
+def test_invalidate_after_writes_through_data():
+    """Writes through `.data` do not bump the version counter the upload cache keys on: `invalidate()` forces the re-upload."""
+    m, z = v1_model()
+    c = torch.from_numpy(z["c"]).to(DEV)
+    with torch.no_grad():
+        y0 = m(c)
+        saved = m.output_conv[1].bias.data.clone()
+        m.output_conv[1].bias.data.add_(0.25)
+        m.invalidate()
+        y1 = m(c)
+        gf = m.graphed(c)
+        assert torch.equal(gf(c), y1)
+        m.output_conv[1].bias.data.copy_(saved)
+        m.invalidate()
+        y2 = m(c)
+        assert torch.equal(gf(c), y2)                                        # the graph re-captures on the new epoch
+    assert not torch.equal(y0, y1) and torch.equal(y0, y2)
