@@ -36,10 +36,14 @@
 namespace vtts {
 namespace tc {
 
-constexpr int CH_COLS = 120;       // accumulator columns (time groups) per tile; divisible by every supported dilation
-constexpr int CH_N = 128;          // UMMA N (columns 120..127 are scratch)
+// Two tile geometries (template parameter NS = tile slots in flight):
+//   NS = 2: two tiles of 120 accumulator columns (UMMA N = 128), the epilogue of one overlaps the MMAs of the other;
+//   NS = 1: one tile of 240 columns (UMMA N = 256, all 512 TMEM columns): no overlap, but half the recomputed halo per valid
+//           position and half the MMA count - wins where the halo is a large part of a 120-column tile (64 channels, k = 7 / 11).
 constexpr int CH_G = 16;           // zero guard rows in front of / behind the data rows of an operand plane
-constexpr int CH_NR = 160;         // rows per operand plane: 16 + 128 + 16
+__host__ __device__ constexpr int ch_cols(int ns) { return ns == 2 ? 120 : 240; }   // live accumulator columns per tile (divisible by the dilations)
+__host__ __device__ constexpr int ch_n(int ns) { return ns == 2 ? 128 : 256; }      // UMMA N (the last 8 / 16 columns are scratch)
+__host__ __device__ constexpr int ch_nr(int ns) { return CH_G + ch_n(ns) + CH_G; }  // rows per operand plane
 constexpr int CH_EPI_WARPS = 16;   // 4 per TMEM lane quarter, each owns 32 accumulator columns
 constexpr int CH_THREADS = (CH_EPI_WARPS + 3) * 32;   // + weight loader + one MMA issuer per tile slot
 constexpr int CH_MAX_SLOTS = 8;    // weight ring slots
@@ -75,9 +79,11 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
     return v;
 }
 
-template <int C, int FMT>
+template <int C, int FMT, int NS>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
+    constexpr int CH_COLS = ch_cols(NS), CH_N = ch_n(NS), CH_NR = ch_nr(NS);
+    constexpr int CPW = CH_N / 4;                   // accumulator columns per epilogue warp
     constexpr int PH = 128 / C, LOGPH = PH == 4 ? 2 : 1;
     constexpr int ROWB = C * 2;                     // bytes per operand row (one position, C channels)
     constexpr int KSTEPS = C / 16;
@@ -88,7 +94,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("vtts: smem base not 1024-byte aligned\n"); __trap(); }
     uint8_t *s_op = smem;
-    uint8_t *s_w = smem + 2 * OPNDB;
+    uint8_t *s_w = smem + NS * OPNDB;
     const int slot_blocks = p.sps + PH - 1;
     const size_t wbytes = p.resident ? (size_t)p.blocks_total * BLKB : (size_t)p.n_slots * slot_blocks * BLKB;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + wbytes);
@@ -111,12 +117,12 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
     if (threadIdx.x == 0) {
         mbar_init(&opnd_full[0], CH_EPI_WARPS); mbar_init(&opnd_full[1], CH_EPI_WARPS);
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-        for (int s = 0; s < CH_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }   // both issuers release a stage
+        for (int s = 0; s < CH_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], NS); }   // every issuer releases a stage
         fence_barrier_init();
     }
     if (warp == WARP_MMA) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     // operand planes start as zeros: the guard rows are never written again
-    for (int i = threadIdx.x; i < 2 * OPNDB / 16; i += CH_THREADS) reinterpret_cast<uint4 *>(s_op)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < NS * OPNDB / 16; i += CH_THREADS) reinterpret_cast<uint4 *>(s_op)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < p.n_convs * C; i += CH_THREADS) s_bias[i] = __ldg(p.bias + i);
     for (int e = threadIdx.x; e < p.n_convs * PH * CH_N; e += CH_THREADS) {
         const int col = e & (CH_N - 1), php = (e / CH_N) & (PH - 1), i = e / (CH_N * PH);
@@ -149,9 +155,11 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_items = trimming ? s_ioff[p.B] : p.total_items;
-    const int G2 = 2 * (int)gridDim.x;
-    // this CTA's j-th item (pairs of neighbouring tiles share their halo lines in L2)
-    auto item_li = [&](int j) { return (j >> 1) * G2 + 2 * (int)blockIdx.x + (j & 1); };
+    const int G2 = NS * (int)gridDim.x;
+    // this CTA's j-th item (NS = 2: pairs of neighbouring tiles share their halo lines in L2)
+    auto item_li = [&](int j) { return (j / NS) * G2 + NS * (int)blockIdx.x + (j % NS); };
+    // TMEM: NS = 2: slot s owns columns [256 s, 256 s + 256) = X (128) + XT (128); NS = 1: X = [0, 256), XT = [256, 512)
+    auto acc_col = [&](int s, bool is_x) { return tmem_base + (uint32_t)(NS == 2 ? s * 256 + (is_x ? 0 : 128) : (is_x ? 0 : 256)); };
     struct Item { int b, T0; };
     auto locate = [&](int li, int &bhint) {
         Item it;
@@ -176,7 +184,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                 for (int q = 0; q < p.blocks_total; ++q) tma_load_2d(s_w + (size_t)q * BLKB, &tm_w, &w_full[0], 0, q * C);
             } else {
                 uint32_t slot = 0, par = 0;
-                for (int j = 0; item_li(j) < n_items; j += 2)
+                for (int j = 0; item_li(j) < n_items; j += NS)
                     for (int i = 0; i < p.n_convs; ++i)
                         for (int st = 0; st < p.spc; ++st) {
                             mbar_wait(&w_empty[slot], par ^ 1u);
@@ -190,7 +198,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                         }
             }
         }
-    } else if (warp == WARP_MMA || warp == WARP_MMA + 1) {
+    } else if (warp == WARP_MMA || (NS == 2 && warp == WARP_MMA + 1)) {
         // ===== MMA issuers: one warp per tile slot.  A single warp issued the MMAs of both tiles back to back and was
         // issue-bound (~95 cycles per N=128 MMA against 64 on the tensor pipe); two warps on two schedulers overlap their
         // issue overhead.  Each warp runs its loop converged with warp-uniform operands (a single-lane loop pays an R2UR
@@ -207,7 +215,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
         // first slice: s' = PH - 1 + half, descending
         const int sp0 = PH - 1 + ch_half;
         const int r0 = sp0 & (PH - 1), q0 = sp0 >> LOGPH;
-        for (int j = 0; item_li(j) < n_items; j += 2) {
+        for (int j = 0; item_li(j) < n_items; j += NS) {
             const bool has = s == 0 || item_li(j + 1) < n_items;   // an odd last pair: slot 1 only keeps the ring in step
             if (!has && p.resident) break;
             for (int i = 0; i < p.n_convs; ++i) {
@@ -216,9 +224,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                     mbar_wait(&opnd_full[s], nf & 1u);
                     ++nf;
                     tc_fence_after();
-                    if (lane == 0) CH_TRACE(j >> 1, s, i * 4 + 2);
+                    if (lane == 0) CH_TRACE(j / NS, s, i * 4 + 2);
                 }
-                const uint32_t tmem_d = tmem_base + (uint32_t)s * 256u + (p.cx[i] ? 0u : 128u);
+                const uint32_t tmem_d = acc_col(s, p.cx[i] != 0);
                 uint32_t acc = p.cx[i] ? 1u : 0u;
                 uint64_t b = op_desc + (uint64_t)r0 * PLANE16 + (uint64_t)CH_G * ROW16 + (uint64_t)q0 * dstep;
                 int r = r0;
@@ -250,25 +258,25 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                 }
                 if (has) {
                     umma_commit_elect(&acc_full[s]);
-                    if (lane == 0) CH_TRACE(j >> 1, s, i * 4 + 3);
+                    if (lane == 0) CH_TRACE(j / NS, s, i * 4 + 3);
                 }
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < CH_EPI_WARPS) {
         // ===== epilogue warps: quarter q of the TMEM lanes = rows 32q .. 32q+31 = (phase, channel) =====
         // (instruction-lean on purpose: 16 warps x 6 convs per tile made this kernel issue-bound - interior tiles take
         // paths without per-element bounds checks, the position -> operand-row map comes from a table)
         const int quarter = warp & 3, part = warp >> 2;
         const int ph = C == 32 ? quarter : (quarter >> 1);
         const int chq = C == 32 ? 0 : (quarter & 1) * 32;          // first channel of this quarter
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int col_lo = part * 32;
-        const int ncol = col_lo + 32 <= CH_COLS ? 32 : CH_COLS - col_lo;   // live accumulator columns of this warp
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const int col_lo = part * CPW;
+        const int ncol = col_lo + CPW <= CH_COLS ? CPW : CH_COLS - col_lo;   // live accumulator columns of this warp
         const int fc = (lane & 3) * 2;                              // fragment: first column
         const int mrow = lane & 7;                                  // stmatrix: operand row this thread addresses
         const uint32_t mchunk = (uint32_t)(chq / 8 + (lane >> 3));  // 16-byte chunk (8 channels) of matrix lane/8
-        const uint32_t op_base[2] = {smem_u32(s_op), smem_u32(s_op + OPNDB)};
+        const uint32_t op_base[2] = {smem_u32(s_op), smem_u32(s_op + (NS - 1) * OPNDB)};
         const int bfr = chq + (lane >> 2);                          // fragment row -> channel (rows fr, fr+8, fr+16, fr+24)
         uint32_t na[2] = {0u, 0u};
         Item cur[2] = {{0, 0}, {0, 0}};
@@ -289,7 +297,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
             const uint16_t *tab = s_tab + (nxt * PH + ph) * CH_N + col_lo + mrow;
             const float slope = p.slope;
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
+            for (int g8 = 0; g8 < CPW / 8; ++g8) {
                 if (g8 * 8 >= ncol) break;
                 const int col = col_lo + g8 * 8;
                 uint32_t ra[4], rb[4];
@@ -320,35 +328,46 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
         // x tile (fp32 channels-last) -> residual accumulator X of slot s; thread = TMEM lane = (phase, channel),
         // register c = accumulator column col_lo + c = position T0 + PH * (col_lo + c) + ph
         auto init_x = [&](int s, const Item &it) {
-            const float *xb = p.x + ((long long)it.b * p.L + it.T0 + ph + PH * col_lo) * C + chq + lane;
-            uint32_t v[32];
-            if (it.T0 >= 0 && it.T0 + W <= p.L && ncol == 32) {
+#pragma unroll 1
+            for (int h = 0; h < CPW / 32; ++h) {
+                const int c0 = col_lo + 32 * h;                       // this pass: accumulator columns c0 .. c0 + 31
+                const int nc32 = ncol - 32 * h < 32 ? ncol - 32 * h : 32;
+                if (nc32 <= 0) break;
+                const float *xb = p.x + ((long long)it.b * p.L + it.T0 + ph + PH * c0) * C + chq + lane;
+                uint32_t v[32];
+                if (it.T0 >= 0 && it.T0 + W <= p.L && nc32 == 32) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(ld_stream_f32(xb + c * (PH * C)));
-            } else {
-                // live columns: c < ncol and 0 <= T0 + PH * (col_lo + c) + ph < L
-                const int base_t = it.T0 + ph + PH * col_lo;
-                int c_lo = base_t >= 0 ? 0 : (-base_t + PH - 1) >> LOGPH;
-                int c_hi = (p.L - base_t + PH - 1) >> LOGPH;
-                c_hi = p.L <= base_t ? 0 : (c_hi < ncol ? c_hi : ncol);
+                    for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(ld_stream_f32(xb + c * (PH * C)));
+                } else {
+                    // live columns: c < nc32 and 0 <= T0 + PH * (c0 + c) + ph < L
+                    const int base_t = it.T0 + ph + PH * c0;
+                    int c_lo = base_t >= 0 ? 0 : (-base_t + PH - 1) >> LOGPH;
+                    int c_hi = (p.L - base_t + PH - 1) >> LOGPH;
+                    c_hi = p.L <= base_t ? 0 : (c_hi < nc32 ? c_hi : nc32);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = (c >= c_lo && c < c_hi) ? __float_as_uint(ld_stream_f32(xb + c * (PH * C))) : 0u;
+                    for (int c = 0; c < 32; ++c) v[c] = (c >= c_lo && c < c_hi) ? __float_as_uint(ld_stream_f32(xb + c * (PH * C))) : 0u;
+                }
+                tmem_st_32x32(acc_col(s, true) + lane_off + (uint32_t)c0, v);
             }
-            tmem_st_32x32(t_lane + (uint32_t)s * 256u + (uint32_t)col_lo, v);
             tmem_st_wait();
         };
         // residual accumulator X of slot s -> global (the block's output, combined into the MRF sum)
         auto final_out = [&](int s, const Item &it, const float *bias_last) {
-            // valid columns of this warp: tile-relative position PH * (col_lo + c) + ph in [halo, min(halo + V, L - T0))
+          const float bv = bias_last[chq + lane];
+#pragma unroll 1
+          for (int h = 0; h < CPW / 32; ++h) {
+            const int c0 = col_lo + 32 * h;                           // this pass: accumulator columns c0 .. c0 + 31
+            const int nc32 = ncol - 32 * h < 32 ? ncol - 32 * h : 32;
+            if (nc32 <= 0) break;
+            // valid columns: tile-relative position PH * (c0 + c) + ph in [halo, min(halo + V, L - T0))
             const int hi_tau = p.halo + p.V < p.L - it.T0 ? p.halo + p.V : p.L - it.T0;
-            const int rel = ph + PH * col_lo;
+            const int rel = ph + PH * c0;
             int c_lo = p.halo <= rel ? 0 : (p.halo - rel + PH - 1) >> LOGPH;
             int c_hi = hi_tau <= rel ? 0 : (hi_tau - rel + PH - 1) >> LOGPH;
-            if (c_hi > ncol) c_hi = ncol;
-            if (c_lo >= c_hi) return;
-            const float bv = bias_last[chq + lane];
+            if (c_hi > nc32) c_hi = nc32;
+            if (c_lo >= c_hi) continue;
             uint32_t v[32];
-            tmem_ld_32x32(t_lane + (uint32_t)s * 256u + (uint32_t)col_lo, v);
+            tmem_ld_32x32(acc_col(s, true) + lane_off + (uint32_t)c0, v);
             const long long base = ((long long)it.b * p.L + it.T0 + rel) * C + chq + lane;
             const bool full = c_lo == 0 && c_hi == 32;
             constexpr int CS = PH * C;                              // floats between two columns of one phase
@@ -389,12 +408,13 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                     }
                 }
             }
+          }
         };
         // L2 prefetch of the x (and MRF-sum) ranges of this CTA's NEXT pair of tiles: their first touch is init_x, whose
         // latency nothing hides (both slots reach the end of their chains together)
         auto prefetch_pair = [&](int j) {
             int bh = bhint;
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NS; ++s) {
                 const int li = item_li(j + s);
                 if (li >= n_items) break;
                 const Item it = locate(li, bh);
@@ -407,43 +427,43 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
         };
 
         const int last = p.n_convs - 1;
-        for (int j = 0;; j += 2) {
+        for (int j = 0;; j += NS) {
             const bool more = item_li(j) < n_items;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NS; ++s) {
                 if (has[s]) {                                       // the previous item of this slot: its last conv is done
                     mbar_wait_relaxed(&acc_full[s], na[s] & 1u);
                     ++na[s];
                     tc_fence_after();
-                    if (warp == 0 && lane == 0) CH_TRACE((j >> 1) - 1, s, 26);
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS - 1, s, 26);
                     final_out(s, cur[s], s_bias + last * C);
-                    if (warp == 0 && lane == 0) CH_TRACE((j >> 1) - 1, s, 27);
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS - 1, s, 27);
                     has[s] = false;
                 }
                 if (more && item_li(j + s) < n_items) {
                     cur[s] = locate(item_li(j + s), bhint);
                     has[s] = true;
-                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, 24);
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS, s, 24);
                     init_x(s, cur[s]);
-                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, 25);
-                    build_operand(s, t_lane + (uint32_t)s * 256u, 1, 65536u, nullptr, 0, cur[s]);
-                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, 28);
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS, s, 25);
+                    build_operand(s, acc_col(s, true) + lane_off, 1, 65536u, nullptr, 0, cur[s]);
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS, s, 28);
                 }
             }
             if (!more) break;
-            if (warp == 0 && lane == 0) prefetch_pair(j + 2);
+            if (warp == 0 && lane == 0) prefetch_pair(j + NS);
             for (int i = 0; i < last; ++i) {
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < NS; ++s) {
                     if (!has[s]) continue;
                     mbar_wait_relaxed(&acc_full[s], na[s] & 1u);
                     ++na[s];
                     tc_fence_after();
                     const bool from_x = p.cx[i] != 0;
-                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, i * 4 + 0);
-                    build_operand(s, t_lane + (uint32_t)s * 256u + (from_x ? 0u : 128u), from_x ? 1 : p.cd[i],
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS, s, i * 4 + 0);
+                    build_operand(s, acc_col(s, from_x) + lane_off, from_x ? 1 : p.cd[i],
                                   from_x ? 65536u : p.cmagic[i], s_bias + i * C, i + 1, cur[s]);
-                    if (warp == 0 && lane == 0) CH_TRACE(j >> 1, s, i * 4 + 1);
+                    if (warp == 0 && lane == 0) CH_TRACE(j / NS, s, i * 4 + 1);
                 }
             }
         }
@@ -499,13 +519,14 @@ static int chain_ph(const ChainSpec &s) { return 128 / s.C; }
 // shared-memory plan: resident weights when the whole block fits next to the operand planes, else a ring of
 // (sps + PH - 1)-block stages with at least one stage of prefetch beyond a whole conv
 struct ChainPlan { int sps, spc, n_slots, resident, blocks_total; size_t smem; bool ok; };
-static ChainPlan chain_plan(const ChainSpec &s) {
+static ChainPlan chain_plan(const ChainSpec &s, int ns) {
     ChainPlan pl{};
+    const int CH_NR = ch_nr(ns), CH_N = ch_n(ns);
     const int PH = chain_ph(s), rowb = s.C * 2;
     const int n_convs = s.n_units * (s.has2 ? 2 : 1);
     const int nsl = s.k + PH - 1;
     const size_t blkb = (size_t)s.C * rowb;
-    const size_t opnd = 2 * (size_t)PH * CH_NR * rowb;
+    const size_t opnd = (size_t)ns * PH * CH_NR * rowb;
     const size_t fixed = (4 + 2 * CH_MAX_SLOTS) * 8 + 16 + (size_t)CH_MAX_CONVS * s.C * 4 + (2 * CH_MAX_TRIM_BATCH + 2) * 4 +
                          (size_t)CH_MAX_CONVS * PH * CH_N * 2 + 64;
     pl.blocks_total = n_convs * nsl + PH - 1;
@@ -526,7 +547,7 @@ static ChainPlan chain_plan(const ChainSpec &s) {
         if (n_slots > CH_MAX_SLOTS) n_slots = CH_MAX_SLOTS;
         // (the two MMA issuers walk the stages of a conv side by side and release each stage together: a ring of three
         // stages keeps one load in flight; it need not hold a whole conv)
-        if (n_slots >= 3 || (n_slots >= 2 && sps == 1)) {
+        if (n_slots >= 3 || (n_slots >= 2 && (sps == 1 || ns == 1))) {
             pl.resident = 0; pl.sps = sps; pl.spc = spc; pl.n_slots = n_slots;
             pl.smem = opnd + (size_t)n_slots * slotb + fixed;
             pl.ok = true;
@@ -542,25 +563,48 @@ static bool chain_enabled() {
     return on == 1;
 }
 
-bool chain_spec_usable(const ChainSpec &s) {
+static bool chain_geometry_usable(const ChainSpec &s, int ns) {
     if (!chain_enabled()) return false;
     if (s.C != 32 && s.C != 64) return false;
     if (s.k < 1 || s.k % 2 == 0 || s.n_units < 1 || s.n_units > 3) return false;
-    const int PH = chain_ph(s), half = (s.k - 1) / 2;
+    const int PH = chain_ph(s), half = (s.k - 1) / 2, cols = ch_cols(ns);
     const int qmax = (half + PH - 1) / PH;                                  // |q| of every slice: s' in [-half, half + PH - 1]
     int halo = 0;
     for (int u = 0; u < s.n_units; ++u) {
         const int d = s.dil[u];
-        if (d < 1 || CH_COLS % d != 0 || qmax * d > CH_G) return false;
+        if (d < 1 || cols % d != 0 || qmax * d > CH_G) return false;
         // without the second conv the dilated conv itself would accumulate onto the residual accumulator, whose columns
         // are laid out for dilation 1: such blocks (vits2 ResBlock2, use_additional_convs=False) keep the per-unit kernels
         if (!s.has2 && d != 1) return false;
         halo += half * d + (s.has2 ? half : 0);
     }
     if (qmax > CH_G) return false;
-    if (PH * CH_COLS - 2 * halo < PH * CH_COLS / 4) return false;          // recompute would dominate
-    return chain_plan(s).ok;
+    if (PH * cols - 2 * halo < PH * cols / 4) return false;                // recompute would dominate
+    return chain_plan(s, ns).ok;
 }
+
+// Tile geometry for a block: 2 = two 120-column tiles in flight, 1 = one 240-column tile, 0 = the chain kernel cannot run it.
+// Cost model per valid position (cycles, from the in-kernel trace): conv hand-over E = 1100 per 128 columns (TMEM read
+// bound), M = 64 cycles per N=128 MMA, 5300 per tile of drain / reload / first build.  With two tiles in flight E and M
+// overlap, with one wide tile they add up but the halo is paid once per 240 columns.  VTTS_CHAIN_NS=1|2 forces a geometry.
+static int chain_pick_ns(const ChainSpec &s) {
+    static int force = -1;
+    if (force < 0) { const char *e = getenv("VTTS_CHAIN_NS"); force = e ? atoi(e) : 0; }
+    const bool ok2 = chain_geometry_usable(s, 2), ok1 = chain_geometry_usable(s, 1);
+    if (force == 1 || force == 2) return (force == 1 ? ok1 : ok2) ? force : (ok2 ? 2 : (ok1 ? 1 : 0));
+    if (!ok1 || !ok2) return ok2 ? 2 : (ok1 ? 1 : 0);
+    const int PH = chain_ph(s), half = (s.k - 1) / 2;
+    const int n_convs = s.n_units * (s.has2 ? 2 : 1);
+    int halo = 0;
+    for (int u = 0; u < s.n_units; ++u) halo += half * s.dil[u] + (s.has2 ? half : 0);
+    const double E = 1100.0, M = (double)(s.k + PH - 1) * (s.C / 16) * 64.0, Bd = 5300.0;
+    const double v2 = PH * 120 - 2 * halo, v1 = PH * 240 - 2 * halo;
+    const double c2 = (n_convs * (2 * E > 2.5 * M ? 2 * E : 2.5 * M) + 2 * Bd) / (2 * v2);
+    const double c1 = (n_convs * (2 * M + 2 * E) + 2 * Bd) / v1;
+    return c1 < 0.95 * c2 ? 1 : 2;
+}
+
+bool chain_spec_usable(const ChainSpec &s) { return chain_pick_ns(s) != 0; }
 
 int chain_extra_reach(const ChainSpec &s) {
     const int PH = chain_ph(s);
@@ -609,16 +653,16 @@ static int chain_num_sms() {
     return sms;
 }
 
-template <int C, int FMT>
+template <int C, int FMT, int NS>
 static int chain_launch_t(const CUtensorMap &tm, const ChainParams &p, size_t smem, dim3 grid, bool pdl, cudaStream_t st) {
     static bool attr[64] = {};
     int dev = 0;
     VTTS_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr[dev]) {
-        VTTS_CHECK_CUDA(cudaFuncSetAttribute(chain_tc_kernel<C, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
+        VTTS_CHECK_CUDA(cudaFuncSetAttribute(chain_tc_kernel<C, FMT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    VTTS_CHECK_CUDA(launch_kernel_ex(chain_tc_kernel<C, FMT>, grid, dim3(CH_THREADS), smem, st, pdl, 1u, tm, p));
+    VTTS_CHECK_CUDA(launch_kernel_ex(chain_tc_kernel<C, FMT, NS>, grid, dim3(CH_THREADS), smem, st, pdl, 1u, tm, p));
     return VTTS_OK;
 }
 
@@ -626,7 +670,9 @@ int chain_launch(const ChainWeights &cw, int fmt, const ChainRun &r, cudaStream_
     if (!cw.valid) return set_error(VTTS_E_STATE, "chain: weights not packed");
     const ChainSpec &s = cw.spec;
     const int PH = chain_ph(s);
-    const ChainPlan pl = chain_plan(s);
+    const int ns = chain_pick_ns(s);
+    if (!ns) return set_error(VTTS_E_UNSUPPORTED, "chain: unsupported block shape");
+    const ChainPlan pl = chain_plan(s, ns);
     if (!pl.ok) return set_error(VTTS_E_UNSUPPORTED, "chain: no shared-memory plan");
     if (r.slope < 0.f || r.slope > 1.f || r.slope_out < 0.f || r.slope_out > 1.f)
         return set_error(VTTS_E_UNSUPPORTED, "chain: LeakyReLU slope outside [0,1]");
@@ -645,7 +691,7 @@ int chain_launch(const ChainWeights &cw, int fmt, const ChainRun &r, cudaStream_
         halo += half * p.cd[i];
     }
     p.halo = halo;
-    p.V = PH * CH_COLS - 2 * halo;
+    p.V = PH * ch_cols(ns) - 2 * halo;
     p.t_tiles = ceil_div(r.L, p.V);
     const long long total = (long long)p.t_tiles * r.B;
     if (total > 0x3fffffffLL) return set_error(VTTS_E_UNSUPPORTED, "chain: too many tiles");
@@ -662,10 +708,12 @@ int chain_launch(const ChainWeights &cw, int fmt, const ChainRun &r, cudaStream_
         if (rc) return rc;
     }
     const int sms = chain_num_sms();
-    const int pairs = (p.total_items + 1) / 2;
+    const int pairs = (p.total_items + ns - 1) / ns;
     dim3 grid((unsigned)(pairs < sms ? pairs : sms));
-    if (s.C == 32) return fmt == VTTS_FMT_BF16 ? chain_launch_t<32, 0>(tm, p, pl.smem, grid, r.pdl, st) : chain_launch_t<32, 1>(tm, p, pl.smem, grid, r.pdl, st);
-    return fmt == VTTS_FMT_BF16 ? chain_launch_t<64, 0>(tm, p, pl.smem, grid, r.pdl, st) : chain_launch_t<64, 1>(tm, p, pl.smem, grid, r.pdl, st);
+#define VTTS_CHAIN_GO(CC, FF) (ns == 2 ? chain_launch_t<CC, FF, 2>(tm, p, pl.smem, grid, r.pdl, st) : chain_launch_t<CC, FF, 1>(tm, p, pl.smem, grid, r.pdl, st))
+    if (s.C == 32) return fmt == VTTS_FMT_BF16 ? VTTS_CHAIN_GO(32, 0) : VTTS_CHAIN_GO(32, 1);
+    return fmt == VTTS_FMT_BF16 ? VTTS_CHAIN_GO(64, 0) : VTTS_CHAIN_GO(64, 1);
+#undef VTTS_CHAIN_GO
 }
 
 // ---------------------------------------------------------------------------------------------
