@@ -20,6 +20,7 @@ constexpr int GU_WARPS = GU_THREADS / 32;
 constexpr int GU_FRW = 4;                    // frames per warp
 constexpr int GU_FR = GU_WARPS * GU_FRW;     // frames per CTA
 constexpr int GU_DCH = 8;                    // feature chunks of 32 per pass (256 features)
+constexpr int GU_TOK = 32;                   // token rows staged in shared memory per pass (32 x 256 x 4 B = 32 KB)
 
 __global__ void __launch_bounds__(GU_THREADS)
 gauss_upsample_kernel(const float *__restrict__ hs, const long long *__restrict__ ds,
@@ -29,6 +30,8 @@ gauss_upsample_kernel(const float *__restrict__ hs, const long long *__restrict_
     float *s_c = sm;                                   // [T_text] token centres
     float *s_p = sm + T_text;                          // [GU_WARPS][GU_FRW][T_text] probabilities
     __shared__ long long warp_tot[GU_WARPS];
+    __shared__ int s_jlo, s_jhi;                       // union of the warps' token windows (ordered by the barriers below)
+    if (threadIdx.x == 0) { s_jlo = T_text; s_jhi = 0; }
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long *drow = ds + (size_t)b * T_text;
 
@@ -54,100 +57,124 @@ gauss_upsample_kernel(const float *__restrict__ hs, const long long *__restrict_
     }
 
     const int t0 = blockIdx.x * GU_FR + warp * GU_FRW;
-    if (t0 >= T_feats) return;
+    const bool active = t0 < T_feats;                  // (inactive warps of the last frame tile only keep the barriers)
     float *p = s_p + (size_t)warp * GU_FRW * T_text;
     const unsigned char *dm = d_mask ? d_mask + (size_t)b * T_text : nullptr;
 
-    // softmax per frame (layers.py:505-516): lanes stride over tokens
     float tt[GU_FRW], mx[GU_FRW], sum[GU_FRW];
-#pragma unroll
-    for (int f = 0; f < GU_FRW; ++f) {
-        const int t = t0 + f;
-        float tv = (float)t;
-        if (h_mask && t < T_feats) tv = tv * (h_mask[(size_t)b * T_feats + t] ? 1.0f : 0.0f);   // t = t * h_masks.float()
-        tt[f] = tv;
-        mx[f] = -INFINITY;
-    }
-    for (int j = lane; j < T_text; j += 32) {
-        const float c = s_c[j];
-        const bool keep = !dm || dm[j];
-#pragma unroll
-        for (int f = 0; f < GU_FRW; ++f) {
-            const float d = tt[f] - c;
-            const float e = keep ? neg_delta * (d * d) : -INFINITY;
-            p[f * T_text + j] = e;
-            mx[f] = fmaxf(mx[f], e);
-        }
-    }
-#pragma unroll
-    for (int f = 0; f < GU_FRW; ++f) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx[f] = fmaxf(mx[f], __shfl_xor_sync(0xffffffffu, mx[f], o));
-        sum[f] = 0.f;
-    }
-    __syncwarp();
-    for (int j = lane; j < T_text; j += 32) {
-#pragma unroll
-        for (int f = 0; f < GU_FRW; ++f) {
-            const float ex = expf(p[f * T_text + j] - mx[f]);   // all -inf row -> NaN, like torch.softmax
-            p[f * T_text + j] = ex;
-            sum[f] += ex;
-        }
-    }
-#pragma unroll
-    for (int f = 0; f < GU_FRW; ++f)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum[f] += __shfl_xor_sync(0xffffffffu, sum[f], o);
-    __syncwarp();
-    // normalise; remember the token window outside of which every probability of these frames is exactly 0 (exp
-    // underflows to 0 beyond |t - c_j| of about 32 frames at delta = 0.1): the weighted sum below skips those tokens,
-    // which adds exact zeros in the reference's matmul - bit-identical for finite hs
     int jlo = T_text, jhi = 0;
-    for (int j = lane; j < T_text; j += 32) {
-        bool nz = false;
+    if (active) {
+        // softmax per frame (layers.py:505-516): lanes stride over tokens
 #pragma unroll
         for (int f = 0; f < GU_FRW; ++f) {
-            const float v = __fdiv_rn(p[f * T_text + j], sum[f]);
-            p[f * T_text + j] = v;
-            nz |= (v != 0.f);                          // (NaN rows - everything masked - stay in the window)
+            const int t = t0 + f;
+            float tv = (float)t;
+            if (h_mask && t < T_feats) tv = tv * (h_mask[(size_t)b * T_feats + t] ? 1.0f : 0.0f);   // t = t * h_masks.float()
+            tt[f] = tv;
+            mx[f] = -INFINITY;
         }
-        if (nz) { jlo = min(jlo, j); jhi = max(jhi, j + 1); }
-    }
+        for (int j = lane; j < T_text; j += 32) {
+            const float c = s_c[j];
+            const bool keep = !dm || dm[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
-        jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
-    }
-    __syncwarp();
+            for (int f = 0; f < GU_FRW; ++f) {
+                const float d = tt[f] - c;
+                const float e = keep ? neg_delta * (d * d) : -INFINITY;
+                p[f * T_text + j] = e;
+                mx[f] = fmaxf(mx[f], e);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < GU_FRW; ++f) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx[f] = fmaxf(mx[f], __shfl_xor_sync(0xffffffffu, mx[f], o));
+            sum[f] = 0.f;
+        }
+        __syncwarp();
+        for (int j = lane; j < T_text; j += 32) {
+#pragma unroll
+            for (int f = 0; f < GU_FRW; ++f) {
+                const float ex = expf(p[f * T_text + j] - mx[f]);   // all -inf row -> NaN, like torch.softmax
+                p[f * T_text + j] = ex;
+                sum[f] += ex;
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < GU_FRW; ++f)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum[f] += __shfl_xor_sync(0xffffffffu, sum[f], o);
+        __syncwarp();
+        // normalise; remember the token window outside of which every probability of these frames is exactly 0 (exp
+        // underflows to 0 beyond |t - c_j| of about 32 frames at delta = 0.1): the weighted sum below skips those tokens,
+        // which adds exact zeros in the reference's matmul - bit-identical for finite hs
+        for (int j = lane; j < T_text; j += 32) {
+            bool nz = false;
+#pragma unroll
+            for (int f = 0; f < GU_FRW; ++f) {
+                const float v = __fdiv_rn(p[f * T_text + j], sum[f]);
+                p[f * T_text + j] = v;
+                nz |= (v != 0.f);                          // (NaN rows - everything masked - stay in the window)
+            }
+            if (nz) { jlo = min(jlo, j); jhi = max(jhi, j + 1); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+            jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+        }
+        __syncwarp();
 
-    // weighted sum: every hs row is read once per GU_FRW frames (layers.py:517)
+        if (lane == 0 && jlo < jhi) { atomicMin(&s_jlo, jlo); atomicMax(&s_jhi, jhi); }
+    }
+    __syncthreads();
+    // weighted sum (layers.py:517).  The 32 frames of this CTA see nearly the same token window: its hs rows are staged in
+    // shared memory by all threads (coalesced, many loads in flight) and every warp accumulates its own sub-window from
+    // there in ascending token order - the same order as before, so the result is bit-identical.  (Per-warp global loads
+    // left the kernel latency-bound: ~1 us per token and warp, 29 us for a single CTA.)
+    const int J0 = s_jlo, J1 = s_jhi;
+    float *s_h = s_p + (size_t)GU_WARPS * GU_FRW * T_text;           // [GU_TOK][dw] staged rows
     const float *hb = hs + (size_t)b * T_text * D;
     for (int d0 = 0; d0 < D; d0 += 32 * GU_DCH) {
+        const int dw = D - d0 < 32 * GU_DCH ? D - d0 : 32 * GU_DCH;  // feature columns of this pass
         float acc[GU_FRW][GU_DCH];
 #pragma unroll
         for (int f = 0; f < GU_FRW; ++f)
 #pragma unroll
             for (int q = 0; q < GU_DCH; ++q) acc[f][q] = 0.f;
-        for (int j = jlo; j < jhi; ++j) {
-            float pj[GU_FRW];
-#pragma unroll
-            for (int f = 0; f < GU_FRW; ++f) pj[f] = p[f * T_text + j];
-            const float *row = hb + (size_t)j * D + d0 + lane;
-#pragma unroll
-            for (int q = 0; q < GU_DCH; ++q) {
-                const float h = (d0 + q * 32 + lane) < D ? __ldg(row + q * 32) : 0.f;
-#pragma unroll
-                for (int f = 0; f < GU_FRW; ++f) acc[f][q] = fmaf(pj[f], h, acc[f][q]);
+        for (int jc = J0; jc < J1; jc += GU_TOK) {
+            const int nt = J1 - jc < GU_TOK ? J1 - jc : GU_TOK;
+            for (int idx = threadIdx.x; idx < nt * dw; idx += GU_THREADS) {
+                const int r = idx / dw, c = idx - r * dw;
+                s_h[r * dw + c] = __ldg(hb + (size_t)(jc + r) * D + d0 + c);
             }
+            __syncthreads();
+            if (active) {
+                const int ja = jlo > jc ? jlo : jc, jb = jhi < jc + nt ? jhi : jc + nt;
+                for (int j = ja; j < jb; ++j) {
+                    float pj[GU_FRW];
+#pragma unroll
+                    for (int f = 0; f < GU_FRW; ++f) pj[f] = p[f * T_text + j];
+                    const float *row = s_h + (j - jc) * dw + lane;
+#pragma unroll
+                    for (int q = 0; q < GU_DCH; ++q) {
+                        const float h = (q * 32 + lane) < dw ? row[q * 32] : 0.f;
+#pragma unroll
+                        for (int f = 0; f < GU_FRW; ++f) acc[f][q] = fmaf(pj[f], h, acc[f][q]);
+                    }
+                }
+            }
+            __syncthreads();
         }
+        if (active) {
 #pragma unroll
-        for (int f = 0; f < GU_FRW; ++f) {
-            const int t = t0 + f;
-            if (t >= T_feats) continue;
-            float *o = out + ((size_t)b * T_feats + t) * D + d0 + lane;
+            for (int f = 0; f < GU_FRW; ++f) {
+                const int t = t0 + f;
+                if (t >= T_feats) continue;
+                float *o = out + ((size_t)b * T_feats + t) * D + d0 + lane;
 #pragma unroll
-            for (int q = 0; q < GU_DCH; ++q)
-                if (d0 + q * 32 + lane < D) o[q * 32] = acc[f][q];
+                for (int q = 0; q < GU_DCH; ++q)
+                    if (q * 32 + lane < dw) o[q * 32] = acc[f][q];
+            }
         }
     }
 }
@@ -163,7 +190,7 @@ extern "C" int vtts_gauss_upsample(const float *hs, const int64_t *ds, const uns
     if (B == 0 || T_feats == 0 || D == 0) return VTTS_OK;
     VTTS_REQUIRE(hs && ds && out, "vtts_gauss_upsample: null pointer");
     VTTS_REQUIRE(T_text >= 1, "vtts_gauss_upsample: T_text must be >= 1");
-    const size_t smem = sizeof(float) * ((size_t)T_text + (size_t)GU_WARPS * GU_FRW * T_text);
+    const size_t smem = sizeof(float) * ((size_t)T_text + (size_t)GU_WARPS * GU_FRW * T_text + (size_t)GU_TOK * 32 * GU_DCH);
     if (smem > 200 * 1024)
         return set_error(VTTS_E_UNSUPPORTED, "vtts_gauss_upsample: T_text %d needs %zu B shared memory", T_text, smem);
     if (smem > 48 * 1024)
