@@ -134,3 +134,40 @@ def test_dropin_install_patches_reference_modules():
         vtts_b200.uninstall()
         del sys.modules["fake_text2wav"]
     assert sys.modules["models.gan_tts.hifigan.generator"].HiFiGAN is RefHiFiGAN
+
+
+def test_dropin_install_covers_the_espnet_names_jets_imports():
+    """jets/model.py:12,18 takes HiFiGANGenerator and LengthRegulator from espnet (absent here): with fake espnet modules in
+    place, install() rebinds those names - in the defining modules and in a module that imported them - and uninstall() restores."""
+    import sys
+    import types
+
+    class FakeGen:  # stands for espnet2.gan_tts.hifigan.HiFiGANGenerator
+        pass
+
+    class FakeLR:
+        pass
+
+    names = ["espnet2", "espnet2.gan_tts", "espnet2.gan_tts.hifigan", "espnet", "espnet.nets", "espnet.nets.pytorch_backend",
+             "espnet.nets.pytorch_backend.fastspeech", "espnet.nets.pytorch_backend.fastspeech.length_regulator", "fake_jets_model"]
+    saved = {n: sys.modules.get(n) for n in names}
+    try:
+        for n in names:
+            sys.modules[n] = types.ModuleType(n)
+        sys.modules["espnet2.gan_tts.hifigan"].HiFiGANGenerator = FakeGen
+        sys.modules["espnet.nets.pytorch_backend.fastspeech.length_regulator"].LengthRegulator = FakeLR
+        sys.modules["fake_jets_model"].HiFiGANGenerator = FakeGen          # `from espnet2.gan_tts.hifigan import HiFiGANGenerator`
+        sys.modules["fake_jets_model"].LengthRegulator = FakeLR
+        vtts_b200.install(import_missing=False)
+        assert sys.modules["fake_jets_model"].HiFiGANGenerator is vtts_b200.HiFiGAN
+        assert sys.modules["fake_jets_model"].LengthRegulator is vtts_b200.LengthRegulator
+        assert sys.modules["espnet2.gan_tts.hifigan"].HiFiGANGenerator is vtts_b200.HiFiGAN
+        vtts_b200.uninstall()
+        assert sys.modules["fake_jets_model"].HiFiGANGenerator is FakeGen and sys.modules["fake_jets_model"].LengthRegulator is FakeLR
+    finally:
+        vtts_b200.uninstall()
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m

@@ -11,6 +11,7 @@ Replaced symbols (reference file:line):
   models/gan_tts/hifigan/layers.py:16      ResidualBlock
   models/tts/fastspeech2/layers.py:410     LengthRegulator      :465 GaussianUpsampling      :571 Postnet
   models/tts/fastspeech2/blocks/transformer.py:265   PositionwiseFeedForward (FFT-block convs of encoder and decoder)
+  espnet2.gan_tts.hifigan.HiFiGANGenerator / espnet ...length_regulator.LengthRegulator  (JETS: jets/model.py:12,18,433,481-496)
   models/gan_tts/vits2/layers.py:107       Generator
   models/gan_tts/vits2/sublayers.py:215    ResBlock1      :312 ResBlock2
   models/gan_tts/vits2/utils.py:111        generate_path (also the name imported into vits2/generator.py:8)
@@ -29,6 +30,11 @@ _TARGETS = {
     "models.tts.fastspeech2.layers": ("LengthRegulator", "GaussianUpsampling", "Postnet"),
     "models.tts.fastspeech2.blocks.transformer": ("PositionwiseFeedForward",),
     "models.gan_tts.jets.alignments": ("GaussianUpsampling",),
+    # JETS takes both classes from espnet (jets/model.py:12,18); the local ones are declared copies of them
+    # (hifigan/generator.py:3, fastspeech2/layers.py:410-462), so the same drop-ins apply when espnet is installed
+    "espnet2.gan_tts.hifigan": ("HiFiGANGenerator",),
+    "espnet2.gan_tts.hifigan.hifigan": ("HiFiGANGenerator",),
+    "espnet.nets.pytorch_backend.fastspeech.length_regulator": ("LengthRegulator",),
     "models.gan_tts.vits2.layers": ("Generator",),
     "models.gan_tts.vits2.sublayers": ("ResBlock1", "ResBlock2"),
     "models.gan_tts.vits2.utils": ("generate_path",),
@@ -40,7 +46,7 @@ def _replacements():
     from . import acoustic, gaussian_upsampling, hifigan, length_regulator, vits2, vits2_path
 
     return {
-        "HiFiGAN": hifigan.HiFiGAN, "ResidualBlock": hifigan.ResidualBlock,
+        "HiFiGAN": hifigan.HiFiGAN, "HiFiGANGenerator": hifigan.HiFiGAN, "ResidualBlock": hifigan.ResidualBlock,
         "LengthRegulator": length_regulator.LengthRegulator, "Generator": vits2.Generator,
         "GaussianUpsampling": gaussian_upsampling.GaussianUpsampling,
         "Postnet": acoustic.Postnet, "PositionwiseFeedForward": acoustic.PositionwiseFeedForward,
