@@ -237,6 +237,13 @@ int vtts_conv_load(VttsConv *c, const float *weight, const float *bias, vtts_str
 int vtts_conv_forward(VttsConv *c, const void *act16, int precision, int B, int L, const float *res, float *out_x,
                       void *out_a16, float slope_out, int act_tanh, vtts_stream_t stream);
 
+/* Conformer convolution module, the part between its two pointwise convs (models/tts/fastspeech2/blocks/conformer.py:470-480):
+ * GLU over the channel halves of pw (B, L, 2C) fp32 channels-last (blocks/utils.py:75-86), depthwise Conv1d(C, C, ksize,
+ * groups = C, "same" zero padding, :532-570) with weights w (C, ksize) and the eval-mode BatchNorm1d folded by the caller into
+ * w / bias (C, or NULL), Swish (blocks/utils.py:63-72); writes the 16-bit operand (B, L, C) of the second pointwise conv. */
+int vtts_dwconv_glu_swish(const float *pw, const float *w, const float *bias, void *out16, int precision, int B, int L, int C,
+                          int ksize, vtts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

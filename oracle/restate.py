@@ -413,3 +413,67 @@ def acoustic_tail_forward(sd: Dict[str, torch.Tensor], frames: torch.Tensor, mel
     if "postnet.convolutions.0.0.conv.weight" in sd:
         outs = postnet_forward(sd, outs, prefix="postnet.") + outs
     return outs.transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------------
+# Conformer decoder (models/tts/fastspeech2/blocks/conformer.py:93-571), eval mode, T <= max_seq_len
+# --------------------------------------------------------------------------------------------
+
+
+def _rel_shift(s: torch.Tensor) -> torch.Tensor:
+    """conformer.py:432-441."""
+    b, h, t1, t2 = s.shape
+    z = s.new_zeros(b, h, t1, 1)
+    return torch.cat([z, s], dim=-1).view(b, h, t2 + 1, t1)[:, :, 1:].view_as(s)
+
+
+def conformer_decoder_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, mask: torch.Tensor, n_head: int,
+                              half_step: bool = True, prefix: str = "", bn_eps: float = 1e-5) -> torch.Tensor:
+    """Decoder.forward (conformer.py:144-169): position table, then per block FFN/2 + rel-MHSA (UNMASKED: the Sequential
+    passes no mask, :252-253) + conv module + FFN/2 + LayerNorm, padded frames zeroed after every block (:254-255)."""
+    B, T, D = x.shape
+    out = x + sd[prefix + "position_enc"][:, :T, :]
+    d_head = D // n_head
+    ffn_f = 0.5 if half_step else 1.0
+
+    def ln(v, p):
+        return F.layer_norm(v, (D,), sd[p + ".weight"], sd[p + ".bias"])
+
+    def ffn(v, p):
+        h = F.linear(ln(v, p + ".sequential.0"), sd[p + ".sequential.1.linear.weight"], sd[p + ".sequential.1.linear.bias"])
+        h = h * torch.sigmoid(h)
+        return F.linear(h, sd[p + ".sequential.4.linear.weight"], sd[p + ".sequential.4.linear.bias"])
+
+    layer = 0
+    while f"{prefix}layer_stack.{layer}.sequential.4.weight" in sd:
+        p = f"{prefix}layer_stack.{layer}.sequential."
+        out = ffn(out, p + "0.module") * ffn_f + out
+        # MultiHeadedSelfAttentionModule (:336-354) + RelativeMultiHeadAttention (:400-430)
+        a = p + "1.module"
+        pos = sd[a + ".positional_encoding"][:, :T, :].expand(B, -1, -1)
+        xin = ln(out, a + ".layer_norm")
+        q = F.linear(xin, sd[a + ".attention.query_proj.linear.weight"]).view(B, T, n_head, d_head)
+        k = F.linear(xin, sd[a + ".attention.key_proj.linear.weight"]).view(B, T, n_head, d_head).permute(0, 2, 1, 3)
+        v = F.linear(xin, sd[a + ".attention.value_proj.linear.weight"]).view(B, T, n_head, d_head).permute(0, 2, 1, 3)
+        pe = F.linear(pos, sd[a + ".attention.pos_proj.linear.weight"]).view(B, T, n_head, d_head)
+        cs = torch.matmul((q + sd[a + ".attention.u_bias"]).transpose(1, 2), k.transpose(2, 3))
+        ps = _rel_shift(torch.matmul((q + sd[a + ".attention.v_bias"]).transpose(1, 2), pe.permute(0, 2, 3, 1)))
+        att = torch.softmax((cs + ps) / float(np.sqrt(D)), -1)
+        ctx = torch.matmul(att, v).transpose(1, 2).reshape(B, T, D)
+        out = F.linear(ctx, sd[a + ".attention.out_proj.linear.weight"]) + out
+        # ConformerConvModule (:470-482)
+        c = p + "2.module.sequential."
+        h = ln(out, c + "0").transpose(1, 2)
+        h = F.conv1d(h, sd[c + "2.conv.weight"], sd[c + "2.conv.bias"])
+        h = h[:, :D] * torch.sigmoid(h[:, D:])
+        wd = sd[c + "4.conv.weight"]
+        h = F.conv1d(h, wd, None, padding=(wd.shape[-1] - 1) // 2, groups=D)
+        h = F.batch_norm(h, sd[c + "5.running_mean"], sd[c + "5.running_var"], sd[c + "5.weight"], sd[c + "5.bias"], False, 0.0, bn_eps)
+        h = h * torch.sigmoid(h)
+        h = F.conv1d(h, sd[c + "7.conv.weight"], sd[c + "7.conv.bias"]).transpose(1, 2)
+        out = h + out
+        out = ffn(out, p + "3.module") * ffn_f + out
+        out = ln(out, p + "4")
+        out = out.masked_fill(mask.unsqueeze(-1), 0)
+        layer += 1
+    return out

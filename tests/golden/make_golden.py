@@ -341,6 +341,42 @@ def acoustic_tail():
     np.savez_compressed(os.path.join(OUT, "acoustic_tail.npz"), **out)
 
 
+def conformer_decoder():
+    """f3, conformer variant: the reference's conformer Decoder (blocks/conformer.py:93-169) built stand-alone.  `small`: full
+    state dict stored (without the position tables); `c4`: the shipped size (6 layers, 384 hidden, 8 heads, k = 31,
+    model_config.yaml:3-6,25-32) drawn with torch.manual_seed(1234): checksums + outputs only."""
+    ref_loader.load_length_regulator()
+    from models.tts.fastspeech2.blocks.conformer import Decoder  # type: ignore
+
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    for tag, (layers, hidden, heads, B, T) in (("small", (2, 64, 2, 3, 45)), ("c4", (6, 384, 8, 2, 70))):
+        cfg = {"decoder_head": heads, "ffn_expansion_factor": 4, "conv_expansion_factor": 2, "conv_kernel_size": 31,
+               "half_step_residual": True, "decoder_dropout": 0.1}
+        torch.manual_seed(1234)
+        dec = Decoder(layers, hidden, 1000, cfg).eval()
+        with torch.no_grad():
+            for i, blk in enumerate(dec.layer_stack):            # non-trivial BatchNorm statistics, as after training
+                bn = blk.sequential[2].module.sequential[5]
+                t = torch.arange(bn.num_features, dtype=torch.float32)
+                bn.running_mean.copy_(0.2 * torch.sin(0.37 * t + i)); bn.running_var.copy_(1.0 + 0.5 * torch.cos(0.11 * t + 2 * i))
+                bn.weight.data.copy_(1.0 + 0.3 * torch.sin(0.05 * t + 3 * i)); bn.bias.data.copy_(0.1 * torch.cos(0.23 * t + i))
+        frames = torch.randn(B, T, hidden, generator=g)
+        mel_len = torch.tensor([T, T - 13, 9][:B])
+        mask = torch.arange(T)[None] >= mel_len[:, None]
+        frames = frames.masked_fill(mask.unsqueeze(-1), 0.0)
+        with torch.no_grad():
+            hs, _ = dec(frames, mask)
+        sd = dec.state_dict()
+        keys = sorted(sd)
+        out.update({f"{tag}.frames": frames.numpy(), f"{tag}.mel_len": mel_len.numpy(), f"{tag}.dec": hs.numpy(),
+                    f"{tag}.keys": np.array(keys), f"{tag}.sums": np.array([float(sd[k].double().sum()) for k in keys])})
+        if tag == "small":
+            out.update(sd_to_np({k: v for k, v in sd.items() if "position" not in k}, prefix="small.sd."))
+        print("conformer_decoder", tag, tuple(hs.shape), len(keys))
+    np.savez_compressed(os.path.join(OUT, "conformer_decoder.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "needs /root/reference"
     only = sys.argv[1:]
@@ -357,6 +393,7 @@ if __name__ == "__main__":
     fastspeech2_capture()
     hifigan_v1_long()
     acoustic_tail()
+    conformer_decoder()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -7,6 +7,7 @@ reference's ``state_dict`` keys, ctypes calls, batch sharding across ranks.
 """
 from . import _lib
 from .acoustic import AcousticTail, ConvNorm, Decoder, FFTBlock, MultiHeadAttention, PositionwiseFeedForward, Postnet
+from .conformer import ConformerBlock, ConformerConvModule, ConformerDecoder
 from .dropin import install, uninstall
 from .gaussian_upsampling import GaussianUpsampling
 from .hifigan import GraphedForward, HiFiGAN, ResidualBlock
@@ -20,6 +21,6 @@ from .vits2_path import expand_by_path, generate_path
 __all__ = [
     "HiFiGAN", "ResidualBlock", "GraphedForward", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
     "Synthesizer", "PendingSynthesis", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall", "generate_path",
-    "expand_by_path", "Decoder", "FFTBlock", "MultiHeadAttention", "PositionwiseFeedForward", "Postnet", "ConvNorm", "AcousticTail", "OneStageTTS", "TwoStageTTS", "save_wav",
+    "expand_by_path", "Decoder", "FFTBlock", "MultiHeadAttention", "PositionwiseFeedForward", "Postnet", "ConvNorm", "AcousticTail", "ConformerDecoder", "ConformerBlock", "ConformerConvModule", "OneStageTTS", "TwoStageTTS", "save_wav",
 ]
 __version__ = "0.1.0"

@@ -60,6 +60,8 @@ SIGNATURES = {
     "vtts_gen_set_valid_lengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vtts_gen_last_launch_count": (C.c_int, [C.c_void_p]),
     "vtts_gen_set_range_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vtts_dwconv_glu_swish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]),
     "vtts_conv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "vtts_conv_destroy": (None, [C.c_void_p]),
     "vtts_conv_padded_channels": (C.c_int, [C.c_void_p]),

@@ -11,6 +11,7 @@ Replaced symbols (reference file:line):
   models/gan_tts/hifigan/layers.py:16      ResidualBlock
   models/tts/fastspeech2/layers.py:410     LengthRegulator      :465 GaussianUpsampling      :571 Postnet
   models/tts/fastspeech2/blocks/transformer.py:265   PositionwiseFeedForward (FFT-block convs of encoder and decoder)
+  models/tts/fastspeech2/blocks/conformer.py:444     ConformerConvModule (convolution module of encoder and decoder blocks)
   espnet2.gan_tts.hifigan.HiFiGANGenerator / espnet ...length_regulator.LengthRegulator  (JETS: jets/model.py:12,18,433,481-496)
   models/gan_tts/vits2/layers.py:107       Generator
   models/gan_tts/vits2/sublayers.py:215    ResBlock1      :312 ResBlock2
@@ -29,6 +30,7 @@ _TARGETS = {
     "models.gan_tts.hifigan.layers": ("ResidualBlock",),
     "models.tts.fastspeech2.layers": ("LengthRegulator", "GaussianUpsampling", "Postnet"),
     "models.tts.fastspeech2.blocks.transformer": ("PositionwiseFeedForward",),
+    "models.tts.fastspeech2.blocks.conformer": ("ConformerConvModule",),
     "models.gan_tts.jets.alignments": ("GaussianUpsampling",),
     # JETS takes both classes from espnet (jets/model.py:12,18); the local ones are declared copies of them
     # (hifigan/generator.py:3, fastspeech2/layers.py:410-462), so the same drop-ins apply when espnet is installed
@@ -43,13 +45,14 @@ _saved: Dict[Tuple[str, str], object] = {}
 
 
 def _replacements():
-    from . import acoustic, gaussian_upsampling, hifigan, length_regulator, vits2, vits2_path
+    from . import acoustic, conformer, gaussian_upsampling, hifigan, length_regulator, vits2, vits2_path
 
     return {
         "HiFiGAN": hifigan.HiFiGAN, "HiFiGANGenerator": hifigan.HiFiGAN, "ResidualBlock": hifigan.ResidualBlock,
         "LengthRegulator": length_regulator.LengthRegulator, "Generator": vits2.Generator,
         "GaussianUpsampling": gaussian_upsampling.GaussianUpsampling,
         "Postnet": acoustic.Postnet, "PositionwiseFeedForward": acoustic.PositionwiseFeedForward,
+        "ConformerConvModule": conformer.ConformerConvModule,
         "ResBlock1": vits2.ResBlock1, "ResBlock2": vits2.ResBlock2, "generate_path": vits2_path.generate_path,
     }
 
