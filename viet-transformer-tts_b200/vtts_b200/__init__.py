@@ -14,6 +14,7 @@ from .hifigan import GraphedForward, HiFiGAN, ResidualBlock
 from .length_regulator import LengthRegulator
 from .sharding import gather_waveforms, plan_shards, shard_batch
 from .synthesis import PendingSynthesis, Synthesizer
+from .training import conv1d_tc, conv_transpose1d_tc, hifigan_forward_tc
 from .tts import OneStageTTS, TwoStageTTS, save_wav
 from .vits2 import Generator, ResBlock1, ResBlock2
 from .vits2_path import expand_by_path, generate_path
@@ -21,6 +22,6 @@ from .vits2_path import expand_by_path, generate_path
 __all__ = [
     "HiFiGAN", "ResidualBlock", "GraphedForward", "LengthRegulator", "GaussianUpsampling", "Generator", "ResBlock1", "ResBlock2",
     "Synthesizer", "PendingSynthesis", "plan_shards", "shard_batch", "gather_waveforms", "install", "uninstall", "generate_path",
-    "expand_by_path", "Decoder", "FFTBlock", "MultiHeadAttention", "PositionwiseFeedForward", "Postnet", "ConvNorm", "AcousticTail", "ConformerDecoder", "ConformerBlock", "ConformerConvModule", "OneStageTTS", "TwoStageTTS", "save_wav",
+    "expand_by_path", "Decoder", "FFTBlock", "MultiHeadAttention", "PositionwiseFeedForward", "Postnet", "ConvNorm", "AcousticTail", "ConformerDecoder", "ConformerBlock", "ConformerConvModule", "OneStageTTS", "TwoStageTTS", "save_wav", "conv1d_tc", "conv_transpose1d_tc", "hifigan_forward_tc",
 ]
 __version__ = "0.1.0"

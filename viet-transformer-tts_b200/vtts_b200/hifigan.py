@@ -89,6 +89,8 @@ class _GeneratorBase(nn.Module):
     """Shared machinery: handle lifetime, weight upload, workspace, kernel forward."""
 
     precision: str = DEFAULT_PRECISION
+    train_backend: str = "eager"      # autograd path: "eager" = the module tree through PyTorch (reference behaviour),
+                                      # "tc" = every conv forward / dgrad on the tcgen05 kernel, wgrad on cuBLAS (training.py)
 
     def _init_runtime(self) -> None:
         self._handles: Dict[int, int] = {}          # device index -> VttsGen*
@@ -469,6 +471,9 @@ class HiFiGAN(_GeneratorBase):
     def forward(self, c: torch.Tensor, g: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(B, in_channels, T) [, (B, global_channels, 1)] -> (B, out_channels, T * upsample_factor)."""
         if self._needs_autograd(c, g):
+            if self.train_backend == "tc":       # generator backward on the kernels (training.py); "eager": PyTorch / cuDNN
+                from .training import hifigan_forward_tc
+                return hifigan_forward_tc(self, c, g)
             return self._forward_eager(c, g)
         return self._run_kernels(c, g)
 
