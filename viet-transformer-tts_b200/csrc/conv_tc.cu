@@ -2789,6 +2789,7 @@ struct VttsConv {
     int cin = 0, cout = 0, k = 0, dil = 1, ci_pad = 0, n_pad = 0;
     uint16_t *w16[2] = {nullptr, nullptr};
     float *bias = nullptr;
+    bool has_bias = false;   // (the allocation is kept when a later load passes no bias: cudaFree would synchronise the device)
     bool loaded = false;
 };
 
@@ -2829,10 +2830,8 @@ extern "C" int vtts_conv_load(VttsConv *c, const float *weight, const float *bia
     if (bias) {
         if (!c->bias) VTTS_CHECK_CUDA(cudaMalloc(&c->bias, (size_t)c->cout * sizeof(float)));
         VTTS_CHECK_CUDA(cudaMemcpyAsync(c->bias, bias, (size_t)c->cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    } else if (c->bias) {
-        cudaFree(c->bias);
-        c->bias = nullptr;
     }
+    c->has_bias = bias != nullptr;
     c->loaded = true;
     return VTTS_OK;
 }
@@ -2847,7 +2846,7 @@ extern "C" int vtts_conv_forward(VttsConv *c, const void *act16, int precision, 
         return set_error(VTTS_E_INVALID, "vtts_conv_forward: precision must be bf16 or fp16");
     const int fmt = precision == VTTS_PRECISION_BF16 ? VTTS_FMT_BF16 : VTTS_FMT_FP16;
     TcConvParams p{};
-    p.bias = c->bias; p.res = res; p.out_x = out_x; p.out_a = (uint16_t *)out_a16; p.out_a_ld = c->cout;
+    p.bias = c->has_bias ? c->bias : nullptr; p.res = res; p.out_x = out_x; p.out_a = (uint16_t *)out_a16; p.out_a_ld = c->cout;
     p.slope_out = slope_out; p.act_tanh = act_tanh; p.x_cl = 1;
     p.n_total = c->cout; p.cout = c->cout; p.L_out = L; p.n_pos = L; p.out_stride = 1; p.out_off0 = 0;
     p.taps = c->k; p.tap_off0 = -(c->k - 1) / 2 * c->dil; p.tap_step = c->dil;
