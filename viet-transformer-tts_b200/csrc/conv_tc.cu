@@ -25,6 +25,7 @@
 #include "tc_common.cuh"
 
 #include <map>
+#include <string>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -2177,6 +2178,34 @@ static bool prof_enabled() {
     if (on < 0) { const char *e = getenv("VTTS_PROFILE"); on = (e && e[0] == '1') ? 1 : 0; }
     return on == 1;
 }
+// VTTS_STAGE_PROFILE=1: CUDA events at the stage boundaries only (programmatic dependent launch stays on, unlike the
+// per-launch VTTS_PROFILE): where the forward's time goes in the pipelined run; printed to stderr after the forward
+struct StageProf {
+    bool on = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    void mark(const char *name, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.emplace_back(name, e);
+    }
+    void report() {
+        if (!on || ev.size() < 2) return;
+        cudaEventSynchronize(ev.back().second);
+        float total = 0.f;
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            fprintf(stderr, "[vtts-stage] %-22s %8.3f ms\n", ev[i].first.c_str(), ms);
+            total += ms;
+        }
+        fprintf(stderr, "[vtts-stage] %-22s %8.3f ms\n", "total", total);
+        for (auto &e : ev) cudaEventDestroy(e.second);
+        ev.clear();
+    }
+};
+static bool stage_prof_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VTTS_STAGE_PROFILE"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
 static void prof_report() {
     if (g_prof.empty()) return;
     cudaDeviceSynchronize();
@@ -2389,6 +2418,9 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         h->launch_count++;
         bias_b = bf.gb;
     }
+    StageProf sp;
+    sp.on = stage_prof_enabled();
+    sp.mark("start", st);
     // input layout change: (B, Cin, T) fp32 -> (B, T, ci_pad) bf16
     const Layer &pre = h->layers[h->idx_pre];
     if ((rc = launch_cf_to_cl_16(c, bf.a_in, B, cfg.in_channels, T, pre.ci_pad, 1.f, fmt, st))) return rc;
@@ -2401,6 +2433,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
         if ((rc = run_conv(h, fmt, pre, bf.a_in, B, T, T, p, st, rate, mg_pre))) return rc;
         if ((rc = dump_f32(0, bf.x_cs, cfg.channels, T))) return rc;
     }
+    sp.mark("layout + input conv", st);
     const uint16_t *cur_a = bf.a_c;
     int L = T;
     for (int i = 0; i < cfg.num_upsamples; ++i) {
@@ -2419,6 +2452,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                     if ((rc = launch_cl_to_cf_f32(bf.x_u, dump_out, B, C, Lo, st))) return rc;
                 }
             }
+            sp.mark((std::string("upsample ") + std::to_string(i)).c_str(), st);
             const int nb = cfg.num_blocks;
             for (int j = 0; j < nb; ++j) {
                 ChainRun r;
@@ -2449,6 +2483,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
                 h->launch_count++;
                 if ((rc = launch_cl_to_cf_f32(bf.x_cs, dump_out, B, C, Lo, st))) return rc;
             }
+            sp.mark((std::string("blocks of stage ") + std::to_string(i) + " (chain)").c_str(), st);
             cur_a = bf.a_c;
             L = Lo;
             continue;
@@ -2460,6 +2495,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
             rate *= u.stride;
             if ((rc = dump_f32(2 * i + 1, bf.x_u, C, Lo))) return rc;
         }
+        sp.mark((std::string("upsample ") + std::to_string(i)).c_str(), st);
         for (int j = 0; j < cfg.num_blocks; ++j) {
             const float *yx = bf.x_u;
             const uint16_t *ya = bf.a_u;
@@ -2501,6 +2537,7 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
             }
         }
         if ((rc = dump_f32(2 * i + 2, bf.x_cs, C, Lo))) return rc;
+        sp.mark((std::string("blocks of stage ") + std::to_string(i)).c_str(), st);
         cur_a = bf.a_c;
         L = Lo;
     }
@@ -2538,6 +2575,8 @@ int tc_forward(VttsGen *h, int fmt, const float *c, const float *g, float *wav, 
             h->launch_count++;
         }
     }
+    sp.mark("output conv", st);
+    sp.report();
     if (prof_enabled()) prof_report();
     return VTTS_OK;
 }
