@@ -9,11 +9,13 @@ torch.manual_seed(1234)
 m = vtts_b200.HiFiGAN().cuda().eval()
 g = torch.Generator().manual_seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 t_end = time.time() + float(sys.argv[2]) if len(sys.argv) > 2 else time.time() + 60
+T_MAX = int(sys.argv[3]) if len(sys.argv) > 3 else 300      # longer rows reach the multi-tile schedules of the chain kernels
+B_MAX = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 n = 0
 with torch.no_grad():
     while time.time() < t_end:
-        B = int(torch.randint(1, 20, (1,), generator=g))
-        T = int(torch.randint(1, 300, (1,), generator=g))
+        B = int(torch.randint(1, B_MAX, (1,), generator=g))
+        T = int(torch.randint(1, T_MAX, (1,), generator=g))
         c = torch.randn(B, 80, T, generator=g).cuda()
         lens = torch.randint(1, T + 1, (B,), generator=g)
         if n % 3 == 0:
