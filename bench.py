@@ -389,19 +389,23 @@ def main():
             sync_total = sum(e2e_ms)
             for _ in range(2):
                 synth.submit(hs_pin, ds_pin).result()
-            torch.cuda.synchronize(dev)
-            barrier()
-            t0 = time.perf_counter()
-            pending = None
-            for k in range(steps):
-                nxt = synth.submit(hs_pin, ds_pin)
-                if pending is not None:
-                    pending.result()
-                pending = nxt
-            wav_h, _ = pending.result()
-            pipe_total = 1e3 * (time.perf_counter() - t0)
-            barrier()
-        return pipe_total, sync_total, wav_h
+            # wall-clock on the host: one stall of the box (another tenant, a page fault in the pinned ring) lands in a
+            # 10-step window as a 2x outlier, so the loop is timed twice and both totals are reported; the line uses the better
+            pipe_totals = []
+            for _rep in range(2):
+                torch.cuda.synchronize(dev)
+                barrier()
+                t0 = time.perf_counter()
+                pending = None
+                for k in range(steps):
+                    nxt = synth.submit(hs_pin, ds_pin)
+                    if pending is not None:
+                        pending.result()
+                    pending = nxt
+                wav_h, _ = pending.result()
+                pipe_totals.append(1e3 * (time.perf_counter() - t0))
+                barrier()
+        return pipe_totals, sync_total, wav_h
 
     def lr_alone(hs, ds, reps=7):
         hs_d, ds_d = hs.to(dev), ds.to(dev)
@@ -473,7 +477,7 @@ def main():
 
     def run_c4(steps):
         gen = make_gen()
-        hs, ds = workload_for("c4", seed=rank, B=32)
+        hs, ds = workload_for("c4", seed=0, B=32)   # weak scaling: the same work on every rank
         r = time_path(gen, hs, ds, steps, 3, 80)
         lr_c4 = lr_alone(hs, ds)
         audio = float(ds.sum()) * HOP / SAMPLE_RATE
@@ -582,7 +586,11 @@ def main():
     # ------------------------------------------------------------------------------------------
     gen = make_gen()
     synth = vtts_b200.Synthesizer(gen, lr, trim_padding=not args.no_trim)
-    hs, ds = make_workload(seed=rank, B=args.batch)
+    # Weak scaling = the SAME per-GPU work on every rank: each rank runs its own copy of the C2 batch (seed 0).  (Up to
+    # round 2's first runs every rank drew its own batch, seed = rank: 7,359 .. 8,534 valid frames per rank, so the
+    # max-over-ranks step time measured the data imbalance - 0.954 at N = 8 by construction - not the hardware;
+    # that variant is still measured below as `detail.distinct_batches_per_rank`.)
+    hs, ds = make_workload(seed=0, B=args.batch)
     hs_pin, ds_pin = hs.pin_memory(), ds.pin_memory()
     valid_frames = int(ds.sum())
     audio_s = valid_frames * HOP / SAMPLE_RATE
@@ -616,9 +624,24 @@ def main():
             eager["note"] = ("PyTorch eager (cuDNN) forward of the same module tree on this GPU, padded batch (16 x %d frames), "
                              "no trim; ours = the untrimmed kernel forward on the same input" % T_out)
     e2e_total, e2e_sync_total, wav_h = time_e2e(synth, hs_pin, ds_pin, args.steps)
+    distinct = None
+    if world > 1:   # transparency: every rank with its OWN random batch (seed = rank): the slowest rank has the most frames
+        hs_r, ds_r = make_workload(seed=rank, B=args.batch)
+        r_r = time_path(gen, hs_r, ds_r, args.steps, args.warmup, 80)
+        ms_r, audio_r, spread_r = reduce_stats(r_r["total_ms"], int(ds_r.sum()) * HOP / SAMPLE_RATE)
+        fr = torch.tensor([float(ds_r.sum())], dtype=torch.float64, device=dev)
+        frs = [torch.zeros_like(fr) for _ in range(world)]
+        dist.all_gather(frs, fr)
+        frs = [int(x.item()) for x in frs]
+        distinct = {"value": audio_r * args.steps / (ms_r / 1e3), "unit": "audio_s/s", "ms_per_step": ms_r / args.steps,
+                    "valid_frames_per_rank": frs, "balance_bound": sum(frs) / (world * max(frs)),
+                    "per_rank_total_ms": spread_r,
+                    "note": "max-over-ranks time with unequal per-rank work: efficiency is capped by balance_bound"}
+        del hs_r, ds_r, r_r
 
     total_ms_all, audio_all, spread = reduce_stats(r["total_ms"], audio_s)
-    e2e_ms_all, _, _ = reduce_stats(e2e_total, 0.0)
+    e2e_reps = [reduce_stats(t, 0.0)[0] for t in e2e_total]     # max over ranks of every repeat
+    e2e_ms_all = min(e2e_reps)
     e2e_sync_ms_all, _, _ = reduce_stats(e2e_sync_total, 0.0)
 
     extra = {}
@@ -672,6 +695,8 @@ def main():
                 "untrimmed_generator_tflops": padded_frames * FLOP_PER_FRAME_V1 / (untrimmed_ms * 1e-3) / 1e12,
                 "untrimmed_audio_s_per_s_valid": audio_s / (untrimmed_ms * 1e-3),
                 "per_rank_total_ms": spread,
+                "per_rank_work": "identical: every rank runs its own copy of the C2 batch (seed 0)",
+                "distinct_batches_per_rank": distinct,
                 "extra": extra,
             },
             "gpu_eager_baseline": eager,
@@ -680,8 +705,10 @@ def main():
                     "h2d_bytes_per_step": hs.numel() * 4 + ds.numel() * 8,
                     "d2h_bytes_per_step": int(wav_h.numel()) * 4 + ds.shape[0] * 8,
                     "ms_per_step": e2e_ms_all / args.steps,
+                    "repeats_ms_per_step": [t / args.steps for t in e2e_reps],
                     "mode": "Synthesizer.submit(): read-back of step k overlaps the kernels of step k+1; every step's "
-                            "inputs and waveform cross PCIe inside the timed region",
+                            "inputs and waveform cross PCIe inside the timed region; host wall clock, K steps timed twice, "
+                            "better of the two (both in repeats_ms_per_step)",
                     "sync_value": audio_all * args.steps / (e2e_sync_ms_all * 1e-3),
                     "sync_note": "Synthesizer.__call__(): one blocking call per step (H2D, kernels, D2H, sync)"},
             "gpu_launches": r["launches"] * args.steps * world,
