@@ -126,6 +126,7 @@ struct TcConvParams {
     int stream_hint;           // 1: activation / residual reads carry the L2 evict-first policy
     int x_cl;                  // out_x is channels-last fp32 [b][t][c] (input of the chain kernel) instead of time-packed
     int act_tanh;              // the 16-bit copy is tanh(value) instead of LeakyReLU(value) (Postnet, layers.py:615-617)
+    int qperm;                 // polyphase rows in quad order (see row_to_phase): 128-bit stores of the time-packed stream
     int reverse;               // walk the tiles last-to-first (alternates per launch: the tail the previous kernel just
                                // wrote is still in L2 when this kernel starts reading there)
     // optional padding trim: tiles whose first position is >= (lens[b] + len_margin) * len_rate + len_extra
@@ -243,6 +244,42 @@ __device__ __forceinline__ void epi_group16_poly(const uint32_t (&v)[16], float 
         if (p.x_cl) px_b[t * p.cout] = val;       // channels-last: the warp's 32 channels are 128 contiguous bytes
         else px_b[(t >> 2) * C4 + (t & 3)] = val;
         if (p.out_a) pa_b[t * p.out_a_ld] = cvt16(lrelu_max(val, p.slope_out), FMT);
+    }
+}
+
+// Quad row order (TcConvParams::qperm): the four lanes of a quad hold the four output samples t = 4 u .. 4 u + 3 of one
+// channel.  A 4 x 4 transpose over the quad (two butterfly steps of shuffles) gives lane r the whole 16-byte slot for
+// positions 4 m + r of the group: four 128-bit stores per thread instead of sixteen 4-byte stores 16 bytes apart (which
+// wrote every 32-byte L2 sector four times: 56 M write sectors for 0.6 GB in the 256 -> 128 upsample).
+__device__ __forceinline__ void quad_transpose4(float &a0, float &a1, float &a2, float &a3, int r) {
+    const bool up = (r & 2) != 0, odd = (r & 1) != 0;
+    float s0 = up ? a0 : a2, s1 = up ? a1 : a3;
+    float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (up) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
+    s0 = odd ? a0 : a1; s1 = odd ? a2 : a3;
+    r0 = __shfl_xor_sync(0xffffffffu, s0, 1); r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (odd) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
+}
+// px_c: out_x + ((b * L4) * C + co) * 4; slot0: time slot (t / 4) of position ibase at phase group q_hi; slot_step = stride / 4
+template <int FMT>
+__device__ __forceinline__ void epi_group16_poly_quad(const uint32_t (&v)[16], float bias, const TcConvParams &p, float *px_c,
+                                                      uint16_t *pa_b /* out_a + b*L_out*lda + co */, int t_first, int slot0,
+                                                      int slot_step, int lane) {
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + bias;
+    if (p.out_a) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pa_b[(t_first + e * p.out_stride) * p.out_a_ld] = cvt16(lrelu_max(f[e], p.slope_out), FMT);
+    }
+    const int r = lane & 3;
+    const int C4 = p.cout * 4;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        quad_transpose4(f[4 * m], f[4 * m + 1], f[4 * m + 2], f[4 * m + 3], r);
+        // this lane: position 4 m + r of the group, samples q_lo = 0 .. 3
+        *reinterpret_cast<float4 *>(px_c + (size_t)(slot0 + (4 * m + r) * slot_step) * C4) =
+            make_float4(f[4 * m], f[4 * m + 1], f[4 * m + 2], f[4 * m + 3]);
     }
 }
 
@@ -589,7 +626,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // with a single m block and no per-batch bias the thread's bias never changes: load it once
         const bool bias_fixed = p.m_blocks == 1 && p.bias_b == nullptr;
         float bias_const = 0.f;
-        if (bias_fixed && p.bias && r_in_copy < p.n_total) bias_const = __ldg(p.bias + (r_in_copy % p.cout));
+        if (bias_fixed && p.bias && r_in_copy < p.n_total) bias_const = __ldg(p.bias + (p.qperm ? (r_in_copy >> 2) % p.cout : r_in_copy % p.cout));
         uint32_t tl = 0;                                    // counts PROCESSED tiles (accumulator ring)
         for (; ti.item < n_items; ti.next(ncl)) {
             tnext.next(ncl);
@@ -602,8 +639,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int nq = n0 + (quarter % qpc) * 32;       // first output row of this warp
             const int n = n0 + r_in_copy;                   // global output row of this thread
             const bool row_ok = n < p.n_total;
-            const int phase = p.n_total == p.cout ? 0 : nq / p.cout;   // warp-uniform (cout is a multiple of 32)
-            const int co = n - phase * p.cout;
+            // output row -> (phase q, channel co).  Phase-major rows: the phase is warp-uniform (cout is a multiple of 32);
+            // quad order: q = 4 q_hi + lane % 4 with a warp-uniform q_hi, 8 channels per warp
+            int phase = p.n_total == p.cout ? 0 : nq / p.cout;
+            int co = n - phase * p.cout;
+            const int q_hi4 = p.qperm ? ((nq >> 2) / p.cout) * 4 : 0;
+            if (p.qperm) { co = (n >> 2) - (q_hi4 >> 2) * p.cout; phase = q_hi4 + (n & 3); }
             float bias = bias_const;
             if (!bias_fixed) {
                 bias = 0.f;
@@ -638,6 +679,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         float *px = X ? p.out_x + (((long long)b * p.L4 + (ibase >> 2)) * p.cout + co) * 4 : nullptr;
                         uint16_t *pa = A ? p.out_a + ((long long)b * p.L_out + ibase) * p.out_a_ld + co : nullptr;
                         epi_group16_dispatch<FMT>(mode, c_ct, v, bias, p, cur, px, pa);
+                    } else if (poly && p.qperm && !p.x_cl && rows_full && ibase + 16 <= p.n_pos &&
+                               (long long)ibase * p.out_stride + p.out_off0 + q_hi4 >= 0 &&
+                               (long long)(ibase + 15) * p.out_stride + p.out_off0 + q_hi4 + 3 < p.L_out) {
+                        // (warp-uniform test over the whole quad: the shuffles inside need all 32 lanes)
+                        epi_group16_poly_quad<FMT>(v, bias, p, p.out_x + ((long long)b * p.L4 * p.cout + co) * 4,
+                                                   A ? p.out_a + (long long)b * p.L_out * p.out_a_ld + co : nullptr,
+                                                   ibase * p.out_stride + p.out_off0 + phase,
+                                                   (ibase * p.out_stride + p.out_off0 + q_hi4) >> 2, p.out_stride >> 2, lane);
                     } else if (poly && rows_full && ibase + 16 <= p.n_pos &&
                                (long long)ibase * p.out_stride + p.out_off0 + phase >= 0 &&
                                (long long)(ibase + 15) * p.out_stride + p.out_off0 + phase < p.L_out) {
@@ -1919,8 +1968,10 @@ static int unit64_prepare(TcUnit64Launch &L, int fmt, const uint16_t *act, int B
 // ---------------------------------------------------------------------------------------------
 // Conv1d (cout,cin,k): n = co, tap j = kernel index.
 // ConvTranspose1d (cin,cout,k), stride s: n = q*cout + co, tap j reads x[i0 - j], weight index q + j*s.
+// qperm (stride and padding multiples of 4): n = ((q / 4) * cout + co) * 4 + q % 4 instead -- the four output samples of one
+// 16-byte slot of the time-packed fp32 stream then live in four neighbouring accumulator lanes (epi_group16_poly_quad).
 __global__ void pack_tc_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int fmt, int kind, int cin,
-                               int cout, int k, int s, int taps, int n_pad, int ci_pad, int n_rows_real) {
+                               int cout, int k, int s, int taps, int n_pad, int ci_pad, int n_rows_real, int qperm) {
     const size_t total = (size_t)taps * n_pad * ci_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int ci = (int)(idx % ci_pad);
@@ -1933,7 +1984,8 @@ __global__ void pack_tc_kernel(const float *__restrict__ w, uint16_t *__restrict
             if (kind == 0) {
                 if (n < cout) v = w[((size_t)n * cin + ci) * k + j];
             } else {
-                const int q = n / cout, co = n - q * cout;
+                int q = n / cout, co = n - q * cout;
+                if (qperm) { const int g = n >> 2, qh = g / cout; co = g - qh * cout; q = qh * 4 + (n & 3); }
                 if (q < s) v = w[((size_t)ci * cout + co) * k + q + j * s];
             }
         }
@@ -2061,13 +2113,17 @@ int tc_pack_layer(VttsGen *h, int layer, cudaStream_t st) {
     const int taps = transposed ? k / s : k;
     l.ci_pad = ci_pad_of(cin);
     l.n_total = transposed ? s * cout : cout;
+    // quad row order: needs t % 4 == q % 4 (stride and padding multiples of 4) and whole channel octets per warp
+    static int quad_on = -1;
+    if (quad_on < 0) { const char *e = getenv("VTTS_TC_QUAD"); quad_on = (e && e[0] == '0') ? 0 : 1; }
+    l.qperm = (quad_on && transposed && s % 4 == 0 && l.padding % 4 == 0 && cout % 8 == 0 && (s * cout) % 128 == 0) ? 1 : 0;
     const int n_pad = pad_to(l.n_total, TM);
     const size_t n = (size_t)taps * n_pad * l.ci_pad;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 8192) blocks = 8192;
     for (int fmt = 0; fmt < 2; ++fmt) {
         if (!l.w16[fmt]) VTTS_CHECK_CUDA(cudaMalloc(&l.w16[fmt], n * sizeof(uint16_t)));
-        pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w16[fmt], fmt, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad, l.n_total);
+        pack_tc_kernel<<<blocks, 256, 0, st>>>(l.w_fold, l.w16[fmt], fmt, l.info.kind, cin, cout, k, s, taps, n_pad, l.ci_pad, l.n_total, l.qperm);
         VTTS_CHECK_LAUNCH();
     }
     if (layer == h->idx_post) {
@@ -2230,6 +2286,7 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
     const int s = transposed ? l.stride : 1;
     p.bias = l.has_bias ? l.bias : nullptr;
     p.n_total = l.n_total;
+    p.qperm = l.qperm;
     p.cout = l.info.cout;
     p.L_out = L_out;
     if (transposed) {
@@ -2795,7 +2852,7 @@ extern "C" int vtts_dbg_conv1d_tc(const float *x, const float *w, const float *b
     int rc = launch_cf_to_cl_16(x, a, B, cin, L, ci_pad, slope_in, fmt, st);
     if (!rc) {
         size_t n = (size_t)ksize * n_pad * ci_pad;
-        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, fmt, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad, cout);
+        pack_tc_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, wp, fmt, 0, cin, cout, ksize, 1, ksize, n_pad, ci_pad, cout, 0);
     }
     if (!rc && res) {
         rc = launch_cf_to_tp4(res, rcl, B, cout, L, st);
@@ -2863,7 +2920,7 @@ extern "C" int vtts_conv_load(VttsConv *c, const float *weight, const float *bia
     if (blocks > 8192) blocks = 8192;
     for (int fmt = 0; fmt < 2; ++fmt) {
         if (!c->w16[fmt]) VTTS_CHECK_CUDA(cudaMalloc(&c->w16[fmt], n * sizeof(uint16_t)));
-        pack_tc_kernel<<<blocks, 256, 0, st>>>(weight, c->w16[fmt], fmt, 0, c->cin, c->cout, c->k, 1, c->k, c->n_pad, c->ci_pad, c->cout);
+        pack_tc_kernel<<<blocks, 256, 0, st>>>(weight, c->w16[fmt], fmt, 0, c->cin, c->cout, c->k, 1, c->k, c->n_pad, c->ci_pad, c->cout, 0);
         VTTS_CHECK_LAUNCH();
     }
     if (bias) {

@@ -18,6 +18,7 @@ struct Layer {
     std::vector<float> w_aux_host;  // the same on the host (passed to conv_post_cl_kernel as kernel parameters)
     int ci_pad = 0;          // bf16 packing: padded input channels
     int n_total = 0;         // bf16 packing: rows per tap (cout, or s*cout for polyphase)
+    int qperm = 0;           // polyphase rows ordered ((q / 4) * cout + co) * 4 + q % 4: four consecutive output samples sit in four neighbouring lanes
     bool has_bias = false;
     bool loaded = false;
 };
