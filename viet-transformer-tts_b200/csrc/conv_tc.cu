@@ -232,18 +232,42 @@ __device__ __forceinline__ void epi_group16_edge(const uint32_t (&v)[16], float 
 
 // Fully valid 16-column group of a polyphase upsample (out_stride > 1; writes fp32 x and the 16-bit copy, no
 // residual): cheap 32-bit index arithmetic relative to per-batch base pointers, no per-element bounds checks.
+// XCL / HAS_A are compile-time so that the 16 stores are straight-line code (one IMAD.WIDE + STG per element): with the
+// flags tested per element the x2 upsamples were ISSUE-bound in this loop (trace: 4.2 k cycles of epilogue per 256-position
+// tile against 1 k cycles of MMAs).
+template <int FMT, bool XCL, bool HAS_A>
+__device__ __forceinline__ void epi_group16_poly_t(const uint32_t (&v)[16], float bias, const TcConvParams &p, float *px_b,
+                                                   uint16_t *pa_b, int t_first) {
+    const int C4 = p.cout * 4;
+    if (XCL) {
+        float *px = px_b + (size_t)t_first * p.cout;              // channels-last: the warp's 32 channels are 128 contiguous bytes
+        const int step = p.out_stride * p.cout;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) px[e * step] = __uint_as_float(v[e]) + bias;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int t = t_first + e * p.out_stride;
+            px_b[(t >> 2) * C4 + (t & 3)] = __uint_as_float(v[e]) + bias;
+        }
+    }
+    if (HAS_A) {
+        uint16_t *pa = pa_b + (size_t)t_first * p.out_a_ld;
+        const int astep = p.out_stride * p.out_a_ld;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pa[e * astep] = cvt16(lrelu_max(__uint_as_float(v[e]) + bias, p.slope_out), FMT);
+    }
+}
 template <int FMT>
 __device__ __forceinline__ void epi_group16_poly(const uint32_t (&v)[16], float bias, const TcConvParams &p,
-                                                 float *px_b /* out_x + (b*L4*C + co)*4 */,
+                                                 float *px_b /* out_x + (b*L4*C + co)*4, or + b*L_out*C + co */,
                                                  uint16_t *pa_b /* out_a + b*L_out*lda + co */, int t_first) {
-    const int C4 = p.cout * 4;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const int t = t_first + e * p.out_stride;
-        const float val = __uint_as_float(v[e]) + bias;
-        if (p.x_cl) px_b[t * p.cout] = val;       // channels-last: the warp's 32 channels are 128 contiguous bytes
-        else px_b[(t >> 2) * C4 + (t & 3)] = val;
-        if (p.out_a) pa_b[t * p.out_a_ld] = cvt16(lrelu_max(val, p.slope_out), FMT);
+    if (p.x_cl) {
+        if (p.out_a) epi_group16_poly_t<FMT, true, true>(v, bias, p, px_b, pa_b, t_first);
+        else epi_group16_poly_t<FMT, true, false>(v, bias, p, px_b, pa_b, t_first);
+    } else {
+        if (p.out_a) epi_group16_poly_t<FMT, false, true>(v, bias, p, px_b, pa_b, t_first);
+        else epi_group16_poly_t<FMT, false, false>(v, bias, p, px_b, pa_b, t_first);
     }
 }
 
@@ -269,8 +293,10 @@ __device__ __forceinline__ void epi_group16_poly_quad(const uint32_t (&v)[16], f
 #pragma unroll
     for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + bias;
     if (p.out_a) {
+        uint16_t *pa = pa_b + (size_t)t_first * p.out_a_ld;
+        const int astep = p.out_stride * p.out_a_ld;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) pa_b[(t_first + e * p.out_stride) * p.out_a_ld] = cvt16(lrelu_max(f[e], p.slope_out), FMT);
+        for (int e = 0; e < 16; ++e) pa[e * astep] = cvt16(lrelu_max(f[e], p.slope_out), FMT);
     }
     const int r = lane & 3;
     const int C4 = p.cout * 4;
@@ -2311,6 +2337,7 @@ static int run_conv(VttsGen *h, int fmt, const Layer &l, const uint16_t *act, in
         if (hint < 0) { const char *e = getenv("VTTS_TC_STREAM_HINT"); hint = (e && e[0] == '0') ? 0 : 1; }
         p.stream_hint = hint;
     }
+    if (g_trace_on >= 100 && h->launch_count == g_trace_on - 100) p.trace = 1;   // debug: pipeline trace of this launch
     TcLaunch L;
     int rc = tc_prepare(L, fmt, act, B, L_in, l.ci_pad, l.w16[fmt], pad_to(l.n_total, TM), p);
     if (rc) return rc;
