@@ -392,19 +392,39 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const ChainParams p) {
                 }
             } else if (p.wr == 1) {
                 float *o = p.cs + base;
+                if (full) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (full || (c >= c_lo && c < c_hi))
+                    for (int c = 0; c < 32; ++c)
                         asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + c * CS), "f"(__uint_as_float(v[c]) + bv + old[c]) : "memory");
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (c >= c_lo && c < c_hi)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + c * CS), "f"(__uint_as_float(v[c]) + bv + old[c]) : "memory");
+                }
             } else {
+                // (interior passes: straight-line stores, the output selection hoisted out of the element loop)
                 float *ox = p.out_x ? p.out_x + base : nullptr;
                 uint16_t *oa = p.out_a ? p.out_a + base : nullptr;
+                float val[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if (full || (c >= c_lo && c < c_hi)) {
-                        const float val = (__uint_as_float(v[c]) + bv + old[c]) * p.scale;
-                        if (ox) ox[c * CS] = val;
-                        if (oa) oa[c * CS] = cvt16(lrelu_fast(val, p.slope_out), FMT);
+                for (int c = 0; c < 32; ++c) val[c] = (__uint_as_float(v[c]) + bv + old[c]) * p.scale;
+                if (full) {
+                    if (ox) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) ox[c * CS] = val[c];
+                    }
+                    if (oa) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) oa[c * CS] = cvt16(lrelu_fast(val[c], p.slope_out), FMT);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (c >= c_lo && c < c_hi) {
+                            if (ox) ox[c * CS] = val[c];
+                            if (oa) oa[c * CS] = cvt16(lrelu_fast(val[c], p.slope_out), FMT);
+                        }
                     }
                 }
             }
