@@ -348,6 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         printf("vtts: dynamic shared memory base not 1024-byte aligned\n");
         __trap();
     }
+    if ((p.trace & 1) && blockIdx.x == 0 && threadIdx.x == 0) g_trace[15] = clock64();          // debug trace: kernel entry
     uint8_t *s_act = smem;
     const uint32_t ACT_STAGES = (uint32_t)p.act_stages, W_STAGES = (uint32_t)p.w_stages;
     uint8_t *s_w = smem + (size_t)ACT_STAGES * ACT_BYTES;
@@ -461,6 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     // programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weight producer never
     // touches data of the previous kernel, so it does not wait at all and fills its ring early.
     if (warp != WARP_W) { grid_dep_wait(); grid_dep_launch(); }
+    if ((p.trace & 1) && blockIdx.x == 0 && threadIdx.x == 0) g_trace[14] = clock64();          // debug trace: previous kernel done
 
     if (warp == WARP_ACT) {
         // ===== activation producer: one (TN + span)-row tile per K chunk, reused by every tap =====
@@ -736,6 +738,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if ((p.trace & 1) && blockIdx.x == 0 && threadIdx.x == 0) g_trace[16 + 15] = clock64();     // debug trace: all roles done
     if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
     if (warp == WARP_MMA) tmem_dealloc(tmem_base, ACC_STAGES * TN);
 }
